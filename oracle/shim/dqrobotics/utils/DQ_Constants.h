@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE — forwards to the dqrobotics stand-in (see ../DQ.h).
+#pragma once
+#include <dqrobotics/DQ.h>
