@@ -1,0 +1,1107 @@
+// pmaf_api.cu — C ABI (include/pmaf.h) over the sm_100a kernels. Host code only orchestrates:
+// buffers, one stream per planner, launches, tiny H2D/D2H copies. There is no CPU compute path:
+// every entry point that computes launches a kernel and fails with PMAF_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/pmaf.h"
+#include "pmaf_rollout.cuh"
+
+using namespace pmaf;
+
+// ---- error plumbing ------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(PMAF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define REQUIRE(cond, code, ...) \
+  do {                           \
+    if (!(cond)) return fail(code, __VA_ARGS__); \
+  } while (0)
+
+extern "C" const char *pmaf_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *pmaf_version(void) { return "pmaf 0.1 sm_100a fp64-exact -fmad=false"; }
+
+// ---- planner object ----------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t resize(size_t count) {
+    if (count == n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr, n = 0;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr, n = 0;
+  }
+};
+
+struct HostOut {  // pinned D2H landing zone
+  EvalResult eval;
+  DeviceBest best;
+  RealState real;
+  unsigned long long steps[2];
+  double real_path[256 * 3];
+};
+
+struct pmaf_planner {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_roll[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][begin/end]
+  bool roll_timing[2] = {false, false};
+  int roll_slot = 0;
+  cudaEvent_t ev_d2h = nullptr, ev_stage = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  bool upload_dedup = true;
+  bool initialized = false;
+  // shard
+  int n_global = 0, first_agent = 0, rank = 0, world = 1;
+  bool shard_set = false;
+  void *nccl = nullptr;
+  // configuration
+  int A = 0, O = 0, H = 0;  // local agents, obstacles, max path points
+  double goal[3] = {0, 0, 0}, mgr_init_pos[3] = {0, 0, 0};
+  double delta_t = 0, pred_dt = 0, shell = 0, mass = 1, rad = 0, vel_max = 0, approach = 0;
+  // device state
+  DevBuf<double> k_attr, k_circ, k_repel, k_damp;  // [n_global]
+  DevBuf<double> init_pos, cur_pos, vel, min_obs, path_len, ws_cost, pred_time, cost, paths, rot, random_vecs;
+  DevBuf<int> n_path, reached;
+  DevBuf<uint32_t> known;
+  DevBuf<double> obs_pos, obs_vel, obs_rad;     // agents' obstacle copy at rollout start
+  DevBuf<double> live_pos, live_vel, live_rad;  // list passed to moveRealEEAgent / resetEEAgents
+  DevBuf<unsigned char> image, real_known;
+  DevBuf<double> real_rot, best_random, scratch, real_path_out;
+  DevBuf<RealState> real;
+  DevBuf<DeviceBest> best;
+  DevBuf<EvalResult> eval;
+  DevBuf<ArgminRecord> rec;
+  DevBuf<unsigned long long> step_counter;
+  DevBuf<unsigned char> l2_scratch;
+  // host mirrors
+  std::vector<double> h_obs_pos, h_obs_vel, h_obs_rad;  // agents' copy
+  std::vector<double> h_live;                            // last uploaded live list (pos|vel|rad)
+  std::vector<double> real_path;
+  std::vector<double> h_random;  // [A][O][3]
+  RealState h_real{};
+  DeviceBest h_best{0, 0, -1, 0};
+  int best_n_obs = 0;
+  EvalResult h_eval{};
+  CostParams last_cost{};
+  bool have_cost = false;
+  bool fused_valid = false;
+  ObstacleImage img{};
+  float margin = 1e-3f;
+  // rollout bookkeeping
+  bool rollout_pending = false;
+  bool obstacles_advanced = false;  // a dynamic rollout advanced the agents' obstacle copies
+  bool agents_touched = true;       // agent state changed since the last rollout launch
+  int known_words = 0;
+  // pinned staging
+  double *h_stage = nullptr;
+  size_t h_stage_doubles = 0;
+  HostOut *h_out = nullptr;
+  bool stage_busy = false;
+  // rng for RandomCfAgent vectors
+  bool seeded = false;
+  uint64_t seed = 0;
+  // tuning + counters
+  int tune_lpa = 0, tune_block = 0;
+  pmaf_counters ctr{};
+};
+
+static int set_device(pmaf_planner *p) {
+  CU(cudaSetDevice(p->device));
+  return 0;
+}
+
+#define ENTER(p)                                              \
+  REQUIRE((p) != nullptr, PMAF_ERR_ARG, "null planner handle"); \
+  if (int rc_ = set_device(p)) return rc_;
+
+#define NEED_INIT(p) REQUIRE((p)->initialized, PMAF_ERR_STATE, "%s: pmaf_init has not been called", __func__)
+
+static PlannerDev make_dev(const pmaf_planner *p) {
+  PlannerDev d{};
+  d.n_agents = p->A, d.first_agent = p->first_agent, d.n_obs = p->O, d.max_steps = p->H;
+  for (int i = 0; i < 3; ++i) d.goal[i] = p->goal[i];
+  d.shell = p->shell, d.mass = p->mass, d.rad = p->rad, d.vel_max = p->vel_max, d.approach_dist = p->approach;
+  d.pred_dt = p->pred_dt;
+  d.k_attr = p->k_attr.p, d.k_circ = p->k_circ.p, d.k_repel = p->k_repel.p, d.k_damp = p->k_damp.p;
+  d.init_pos = p->init_pos.p, d.cur_pos = p->cur_pos.p, d.vel = p->vel.p, d.min_obs_dist = p->min_obs.p;
+  d.path_len = p->path_len.p, d.ws_cost = p->ws_cost.p, d.pred_time_ns = p->pred_time.p;
+  d.n_path = p->n_path.p, d.reached = p->reached.p, d.cost = p->cost.p, d.paths = p->paths.p;
+  d.rot = p->rot.p, d.random_vecs = p->random_vecs.p, d.known = p->known.p, d.known_words = p->known_words;
+  d.image = p->image.p, d.img = p->img;
+  d.fused_cost = p->last_cost, d.fused_valid = p->fused_valid ? 1 : 0;
+  d.step_counter = p->step_counter.p;
+  return d;
+}
+
+static ObstacleImage layout_image(int n_obs, bool dynamic) {
+  ObstacleImage im{};
+  im.n_obs = n_obs, im.dynamic = dynamic ? 1 : 0;
+  const uint32_t col = (uint32_t)(((size_t)n_obs * sizeof(double) + 15) & ~(size_t)15);
+  uint32_t off = 0;
+  im.off_px = off, off += col;
+  im.off_py = off, off += col;
+  im.off_pz = off, off += col;
+  im.off_rs = off, off += col;
+  if (dynamic) {
+    im.off_vx = off, off += col;
+    im.off_vy = off, off += col;
+    im.off_vz = off, off += col;
+    im.off_dx = off, off += col;
+    im.off_dy = off, off += col;
+    im.off_dz = off, off += col;
+  }
+  im.off_bp = off, off += (uint32_t)((size_t)n_obs * sizeof(float4));
+  im.bytes = (off + 15u) & ~15u;
+  return im;
+}
+
+static bool any_nonzero(const std::vector<double> &v) {
+  for (double x : v)
+    if (x != 0.0) return true;
+  return false;
+}
+
+static float broad_phase_margin(const pmaf_planner *p, const double *pos) {
+  double s = 0.0;
+  for (int i = 0; i < 3; ++i) s = std::max({s, std::fabs(p->goal[i]), std::fabs(pos[i]), std::fabs(p->mgr_init_pos[i])});
+  double vmax_obs = 0.0;
+  for (double x : p->h_obs_pos) s = std::max(s, std::fabs(x));
+  for (double x : p->h_obs_vel) vmax_obs = std::max(vmax_obs, std::fabs(x));
+  s += (p->vel_max + vmax_obs * 1.7320508) * p->pred_dt * p->H;
+  if (!std::isfinite(s)) s = 1e6;
+  return (float)(1e-3 + 4e-6 * s);
+}
+
+// wait until the pinned H2D staging buffer may be overwritten
+static int stage_acquire(pmaf_planner *p, size_t doubles) {
+  if (p->stage_busy) {
+    CU(cudaEventSynchronize(p->ev_stage));
+    p->stage_busy = false;
+  }
+  if (doubles > p->h_stage_doubles) {
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    p->h_stage = nullptr, p->h_stage_doubles = 0;
+    CU(cudaMallocHost(&p->h_stage, doubles * sizeof(double)));
+    p->h_stage_doubles = doubles;
+  }
+  return 0;
+}
+static int stage_release(pmaf_planner *p) {
+  CU(cudaEventRecord(p->ev_stage, p->stream));
+  p->stage_busy = true;
+  return 0;
+}
+
+static int h2d(pmaf_planner *p, void *dst, const void *src_pinned, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src_pinned, bytes, cudaMemcpyHostToDevice, p->stream));
+  p->ctr.h2d_bytes += bytes;
+  return 0;
+}
+static int d2h(pmaf_planner *p, void *dst, const void *src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream));
+  p->ctr.d2h_bytes += bytes;
+  return 0;
+}
+
+// collect the device time of finished rollouts (CUDA events recorded around the kernel)
+static int harvest_timing(pmaf_planner *p, int slot, bool wait) {
+  if (!p->roll_timing[slot]) return 0;
+  if (wait) CU(cudaEventSynchronize(p->ev_roll[slot][1]));
+  else if (cudaEventQuery(p->ev_roll[slot][1]) != cudaSuccess) return 0;
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, p->ev_roll[slot][0], p->ev_roll[slot][1]));
+  p->ctr.last_rollout_ms = ms;
+  p->ctr.rollout_ms_total += ms;
+  p->roll_timing[slot] = false;
+  return 0;
+}
+
+static int finish_rollout(pmaf_planner *p) {
+  if (p->rollout_pending) {
+    CU(cudaStreamSynchronize(p->stream));
+    p->rollout_pending = false;
+  }
+  if (int rc = harvest_timing(p, p->roll_slot ^ 1, true)) return rc;
+  return harvest_timing(p, p->roll_slot, true);
+}
+
+// ---- lifecycle -------------------------------------------------------------------------------------------------
+extern "C" int pmaf_create(pmaf_planner **out, int device) {
+  REQUIRE(out != nullptr, PMAF_ERR_ARG, "pmaf_create: out is null");
+  *out = nullptr;
+  int n_dev = 0;
+  CU(cudaGetDeviceCount(&n_dev));
+  REQUIRE(device >= 0 && device < n_dev, PMAF_ERR_CUDA, "pmaf_create: CUDA device %d not available (%d visible)",
+          device, n_dev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  REQUIRE(prop.major == 10, PMAF_ERR_CUDA,
+          "pmaf_create: device %d is sm_%d%d; libpmaf is built for sm_100a only and has no fallback", device,
+          prop.major, prop.minor);
+  pmaf_planner *p = new (std::nothrow) pmaf_planner();
+  REQUIRE(p != nullptr, PMAF_ERR_ALLOC, "pmaf_create: out of host memory");
+  p->device = device;
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s)
+    for (int e = 0; e < 2; ++e) CU(cudaEventCreate(&p->ev_roll[s][e]));
+  CU(cudaEventCreateWithFlags(&p->ev_d2h, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&p->ev_stage, cudaEventDisableTiming));
+  CU(cudaEventCreate(&p->ev_t0));
+  CU(cudaEventCreate(&p->ev_t1));
+  CU(cudaMallocHost(&p->h_out, sizeof(HostOut)));
+  memset(p->h_out, 0, sizeof(HostOut));
+  CU(p->best.resize(1));
+  CU(p->eval.resize(1));
+  CU(p->rec.resize(1));
+  CU(p->real.resize(1));
+  CU(p->step_counter.resize(2));
+  CU(p->scratch.resize(16));
+  CU(cudaMemsetAsync(p->best.p, 0, sizeof(DeviceBest), p->stream));
+  CU(cudaMemsetAsync(p->real.p, 0, sizeof(RealState), p->stream));
+  CU(cudaMemsetAsync(p->step_counter.p, 0, 2 * sizeof(unsigned long long), p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  *out = p;
+  return 0;
+}
+
+extern "C" int pmaf_destroy(pmaf_planner *p) {
+  if (!p) return 0;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  for (DevBuf<double> *b :
+       {&p->k_attr, &p->k_circ, &p->k_repel, &p->k_damp, &p->init_pos, &p->cur_pos, &p->vel, &p->min_obs,
+        &p->path_len, &p->ws_cost, &p->pred_time, &p->cost, &p->paths, &p->rot, &p->random_vecs, &p->obs_pos,
+        &p->obs_vel, &p->obs_rad, &p->live_pos, &p->live_vel, &p->live_rad, &p->real_rot, &p->best_random,
+        &p->scratch, &p->real_path_out})
+    b->release();
+  p->l2_scratch.release();
+  p->n_path.release(), p->reached.release(), p->known.release(), p->image.release(), p->real_known.release();
+  p->real.release(), p->best.release(), p->eval.release(), p->rec.release(), p->step_counter.release();
+  if (p->h_stage) cudaFreeHost(p->h_stage);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  for (cudaEvent_t e : {p->ev_roll[0][0], p->ev_roll[0][1], p->ev_roll[1][0], p->ev_roll[1][1], p->ev_d2h, p->ev_stage, p->ev_t0, p->ev_t1})
+    if (e) cudaEventDestroy(e);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return 0;
+}
+
+extern "C" int pmaf_set_shard(pmaf_planner *p, int n_global, int first_agent, int rank, int world) {
+  ENTER(p);
+  REQUIRE(n_global >= 1 && first_agent >= 0 && first_agent < n_global && world >= 1 && rank >= 0 && rank < world,
+          PMAF_ERR_ARG, "pmaf_set_shard: bad shard (n_global=%d first=%d rank=%d world=%d)", n_global, first_agent,
+          rank, world);
+  p->n_global = n_global, p->first_agent = first_agent, p->rank = rank, p->world = world;
+  p->shard_set = true;
+  return 0;
+}
+
+extern "C" int pmaf_set_nccl_comm(pmaf_planner *p, void *nccl_comm) {
+  ENTER(p);
+  p->nccl = nccl_comm;
+  return 0;
+}
+
+extern "C" int pmaf_seed_random_vecs(pmaf_planner *p, uint64_t seed) {
+  ENTER(p);
+  p->seeded = true, p->seed = seed;
+  return 0;
+}
+
+static int upload_real(pmaf_planner *p) {
+  if (int rc = stage_acquire(p, sizeof(RealState) / sizeof(double))) return rc;
+  memcpy(p->h_stage, &p->h_real, sizeof(RealState));
+  if (int rc = h2d(p, p->real.p, p->h_stage, sizeof(RealState))) return rc;
+  return stage_release(p);
+}
+
+template <class K, class... Args>
+static int launch(pmaf_planner *p, K kernel, dim3 grid, dim3 block, size_t smem, Args... args) {
+  kernel<<<grid, block, smem, p->stream>>>(args...);
+  CU(cudaGetLastError());
+  p->ctr.kernel_launches++;
+  return 0;
+}
+
+// (re)build the staging image and, optionally, reset the agents
+static int launch_reset(pmaf_planner *p, bool do_agents, bool from_real, const double *dev_pos_vel, int n_update,
+                        const double *dev_new_pos, const double *dev_new_vel, bool set_known, bool reset_velocity) {
+  PlannerDev d = make_dev(p);
+  ResetArgs r{};
+  r.pos_vel = dev_pos_vel, r.real = p->real.p, r.from_real = from_real ? 1 : 0;
+  r.n_obs_update = n_update, r.new_pos = dev_new_pos, r.new_vel = dev_new_vel;
+  r.obs_pos = p->obs_pos.p, r.obs_vel = p->obs_vel.p, r.obs_rad = p->obs_rad.p;
+  r.real_known = p->real_known.p, r.image = p->image.p, r.margin = p->margin;
+  r.set_known = set_known ? 1 : 0, r.reset_velocity = reset_velocity ? 1 : 0;
+  r.do_agents = do_agents ? 1 : 0;
+  const int block = 128;
+  const int grid = do_agents ? (p->A + block - 1) / block : 1;
+  return launch(p, reset_kernel, dim3(grid), dim3(block), 0, d, r);
+}
+
+extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, int n_obs, const double *obs_pos,
+                         const double *obs_vel, const double *obs_rad, int n_agents, const double *k_attr,
+                         const double *k_circ, const double *k_repel, const double *k_damp, const double *k_manip,
+                         int n_force, const double *k_repel_force, double velocity_max, double approach_dist,
+                         double detect_shell_rad, uint64_t max_prediction_steps, uint64_t prediction_freq_multiple,
+                         double agent_mass, double radius) {
+  ENTER(p);
+  (void)k_manip, (void)n_force, (void)k_repel_force;  // manipulability / body forces have no caller on this path
+  REQUIRE(goal && obs_pos && obs_vel && obs_rad && k_attr && k_circ && k_repel && k_damp, PMAF_ERR_ARG,
+          "pmaf_init: null array");
+  REQUIRE(n_obs >= 1 && n_obs <= kMaxObstacles, PMAF_ERR_ARG,
+          "pmaf_init: n_obs=%d out of range [1, %d] (the last obstacle is the sentinel)", n_obs, kMaxObstacles);
+  REQUIRE(n_agents >= 0, PMAF_ERR_ARG, "pmaf_init: n_agents=%d", n_agents);
+  REQUIRE(max_prediction_steps >= 1 && max_prediction_steps <= (1u << 24), PMAF_ERR_ARG,
+          "pmaf_init: max_prediction_steps=%llu out of range", (unsigned long long)max_prediction_steps);
+  if (int rc = finish_rollout(p)) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+
+  // at least the HAD agent always exists (cf_manager.cpp:70-72); gains of a missing agent read as 0
+  const int n_glob_in = std::max(n_agents, 1);
+  if (!p->shard_set) p->n_global = n_glob_in, p->first_agent = 0, p->rank = 0, p->world = 1;
+  REQUIRE(p->n_global == n_glob_in, PMAF_ERR_ARG,
+          "pmaf_init: sharded planner expects the GLOBAL gain arrays (n_agents=%d, shard n_global=%d)", n_agents,
+          p->n_global);
+  int n_local = p->n_global;
+  if (p->shard_set) {
+    // contiguous blocks: rank r owns [r*n/w, (r+1)*n/w); first_agent was given by the caller
+    long long next = (long long)(p->rank + 1) * p->n_global / p->world;
+    n_local = (int)(next - p->first_agent);
+    REQUIRE(n_local >= 1, PMAF_ERR_ARG, "pmaf_init: shard of rank %d is empty", p->rank);
+  }
+  p->A = n_local, p->O = n_obs, p->H = (int)max_prediction_steps;
+  for (int i = 0; i < 3; ++i) p->goal[i] = goal[i];
+  p->delta_t = delta_t, p->pred_dt = (double)prediction_freq_multiple * delta_t;
+  p->shell = detect_shell_rad, p->mass = agent_mass, p->rad = radius, p->vel_max = velocity_max;
+  p->approach = approach_dist;
+  p->known_words = (n_obs + 31) / 32;
+  const size_t A = p->A, O = p->O, H = p->H, G = p->n_global;
+
+  CU(p->k_attr.resize(G));
+  CU(p->k_circ.resize(G));
+  CU(p->k_repel.resize(G));
+  CU(p->k_damp.resize(G));
+  CU(p->init_pos.resize(A * 3));
+  CU(p->cur_pos.resize(A * 3));
+  CU(p->vel.resize(A * 3));
+  CU(p->min_obs.resize(A));
+  CU(p->path_len.resize(A));
+  CU(p->ws_cost.resize(A));
+  CU(p->pred_time.resize(A));
+  CU(p->cost.resize(A));
+  CU(p->n_path.resize(A));
+  CU(p->reached.resize(A));
+  CU(p->paths.resize(A * H * 3));
+  CU(p->rot.resize(A * O * 3));
+  CU(p->random_vecs.resize(A * O * 3));
+  CU(p->known.resize(A * p->known_words));
+  CU(p->obs_pos.resize(O * 3));
+  CU(p->obs_vel.resize(O * 3));
+  CU(p->obs_rad.resize(O));
+  CU(p->live_pos.resize(O * 3));
+  CU(p->live_vel.resize(O * 3));
+  CU(p->live_rad.resize(O));
+  CU(p->real_known.resize(O));
+  CU(p->real_rot.resize(O * 3));
+  CU(p->real_path_out.resize(256 * 3));
+  {  // best_agent_ survives init (quirk 6); keep the overlapping part of its random vectors
+    DevBuf<double> old = p->best_random;
+    const int old_n = p->best_n_obs;
+    p->best_random = DevBuf<double>();
+    CU(p->best_random.resize(O * 3));
+    CU(cudaMemsetAsync(p->best_random.p, 0, O * 3 * sizeof(double), p->stream));
+    if (old.p && old_n > 0)
+      CU(cudaMemcpyAsync(p->best_random.p, old.p, (size_t)std::min<int>(old_n, (int)O) * 3 * sizeof(double),
+                         cudaMemcpyDeviceToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    old.release();
+    p->best_n_obs = (int)O;
+  }
+  p->h_live.clear();
+
+  // gains (global), agents' obstacle copy, random vectors
+  p->h_obs_pos.assign(obs_pos, obs_pos + O * 3);
+  p->h_obs_vel.assign(obs_vel, obs_vel + O * 3);
+  p->h_obs_rad.assign(obs_rad, obs_rad + O);
+  {
+    const size_t n = 4 * G + 7 * O;
+    if (int rc = stage_acquire(p, n)) return rc;
+    double *s = p->h_stage;
+    for (size_t i = 0; i < G; ++i) {
+      const bool have = (int)i < n_agents;
+      s[i] = have ? k_attr[i] : 0.0, s[G + i] = have ? k_circ[i] : 0.0;
+      s[2 * G + i] = have ? k_repel[i] : 0.0, s[3 * G + i] = have ? k_damp[i] : 0.0;
+    }
+    memcpy(s + 4 * G, obs_pos, O * 3 * sizeof(double));
+    memcpy(s + 4 * G + 3 * O, obs_vel, O * 3 * sizeof(double));
+    memcpy(s + 4 * G + 6 * O, obs_rad, O * sizeof(double));
+    if (int rc = h2d(p, p->k_attr.p, s, G * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->k_circ.p, s + G, G * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->k_repel.p, s + 2 * G, G * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->k_damp.p, s + 3 * G, G * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->obs_pos.p, s + 4 * G, O * 3 * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->obs_vel.p, s + 4 * G + 3 * O, O * 3 * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->obs_rad.p, s + 4 * G + 6 * O, O * sizeof(double))) return rc;
+    if (int rc = stage_release(p)) return rc;
+  }
+  {  // RandomCfAgent vectors (cf_agent.h:338-342): U[-1,1]^3 normalised, agent-major, obstacle-minor.
+     // The reference seeds a fresh mt19937 from std::random_device per vector
+     // (helper_functions.cpp:8-12); one generator seeded once gives the same distribution.
+    p->h_random.assign(A * O * 3, 0.0);
+    std::mt19937_64 gen(p->seeded ? p->seed : ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}());
+    std::uniform_real_distribution<double> dis(-1.0, 1.0);
+    if (p->seeded) {  // keep streams shard-independent: skip the draws of agents before this shard
+      const unsigned long long skip_agents = p->first_agent > 5 ? p->first_agent - 5 : 0;
+      gen.discard(skip_agents * O * 3);
+    }
+    for (size_t a = 0; a < A; ++a) {
+      if (agent_type_of_index(p->first_agent + (int)a) != RANDOM_AGENT) continue;
+      for (size_t i = 0; i < O; ++i) {
+        v3 r = normalized3(mk3(dis(gen), dis(gen), dis(gen)));
+        st3(&p->h_random[(a * O + i) * 3], r);
+      }
+    }
+    CU(cudaMemcpyAsync(p->random_vecs.p, p->h_random.data(), A * O * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                       p->stream));
+    p->ctr.h2d_bytes += A * O * 3 * sizeof(double);
+    CU(cudaStreamSynchronize(p->stream));
+  }
+
+  // real agent re-created (cf_manager.cpp:66-68): pos = [init_pos_], vel = (0.01,0,0), init_pos_ = 0
+  memset(&p->h_real, 0, sizeof p->h_real);
+  for (int i = 0; i < 3; ++i) p->h_real.pos[i] = p->mgr_init_pos[i];
+  p->h_real.vel[0] = 0.01;
+  p->real_path.assign(p->mgr_init_pos, p->mgr_init_pos + 3);
+  if (int rc = upload_real(p)) return rc;
+  CU(cudaMemsetAsync(p->real_known.p, 0, O, p->stream));
+  {
+    std::vector<double> rr(O * 3, 0.0);
+    for (size_t i = 0; i < O; ++i) rr[3 * i + 2] = 1.0;
+    CU(cudaMemcpyAsync(p->real_rot.p, rr.data(), O * 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+  }
+
+  p->initialized = true;
+  p->fused_valid = false;
+  p->obstacles_advanced = false;
+  p->agents_touched = true;
+  p->img = layout_image((int)O, any_nonzero(p->h_obs_vel));
+  CU(p->image.resize(p->img.bytes));
+  p->margin = broad_phase_margin(p, p->mgr_init_pos);
+
+  // agents constructed at the manager's init_pos_ (cf_manager.cpp:70-104)
+  {
+    if (int rc = stage_acquire(p, 3)) return rc;
+    memcpy(p->h_stage, p->mgr_init_pos, 3 * sizeof(double));
+    if (int rc = h2d(p, p->scratch.p, p->h_stage, 3 * sizeof(double))) return rc;
+    if (int rc = stage_release(p)) return rc;
+    PlannerDev d = make_dev(p);
+    if (int rc = launch(p, init_state_kernel, dim3(296), dim3(256), 0, d, (const double *)p->scratch.p)) return rc;
+  }
+  if (int rc = launch_reset(p, false, false, nullptr, 0, nullptr, nullptr, false, false)) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+extern "C" int pmaf_set_random_vecs(pmaf_planner *p, const double *vecs, int n_agents, int n_obs) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(vecs != nullptr, PMAF_ERR_ARG, "pmaf_set_random_vecs: null array");
+  REQUIRE(n_obs == p->O && (n_agents == p->A || n_agents == p->n_global), PMAF_ERR_ARG,
+          "pmaf_set_random_vecs: expected [%d or %d][%d][3], got [%d][%d][3]", p->A, p->n_global, p->O, n_agents,
+          n_obs);
+  if (int rc = finish_rollout(p)) return rc;
+  const size_t O = p->O;
+  const size_t off = n_agents == p->A ? 0 : (size_t)p->first_agent;  // local table or slice of the global one
+  for (size_t a = 0; a < (size_t)p->A; ++a) {
+    if (agent_type_of_index(p->first_agent + (int)a) != RANDOM_AGENT) continue;
+    memcpy(&p->h_random[a * O * 3], vecs + (off + a) * O * 3, O * 3 * sizeof(double));
+  }
+  CU(cudaMemcpyAsync(p->random_vecs.p, p->h_random.data(), p->h_random.size() * sizeof(double),
+                     cudaMemcpyHostToDevice, p->stream));
+  p->ctr.h2d_bytes += p->h_random.size() * sizeof(double);
+  CU(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+extern "C" int pmaf_get_random_vecs(pmaf_planner *p, double *vecs, int n_agents, int n_obs) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(vecs && n_obs == p->O && n_agents == p->A, PMAF_ERR_ARG, "pmaf_get_random_vecs: expected [%d][%d][3]",
+          p->A, p->O);
+  memcpy(vecs, p->h_random.data(), p->h_random.size() * sizeof(double));
+  return 0;
+}
+
+// ---- per-tick calls ----------------------------------------------------------------------------------------------------
+extern "C" int pmaf_set_initial_position(pmaf_planner *p, const double pos[3]) {
+  ENTER(p);
+  REQUIRE(pos != nullptr, PMAF_ERR_ARG, "pmaf_set_initial_position: null position");
+  for (int i = 0; i < 3; ++i) p->mgr_init_pos[i] = pos[i];
+  if (!p->initialized) return 0;  // default-constructed manager: only init_pos_ is meaningful
+  if (int rc = finish_rollout(p)) return rc;
+  // real agent: init_pos_ := pos and the path is APPENDED to (cf_agent.cpp:34-46)
+  for (int i = 0; i < 3; ++i) p->h_real.init_pos[i] = pos[i], p->h_real.pos[i] = pos[i];
+  p->real_path.insert(p->real_path.end(), pos, pos + 3);
+  if (int rc = upload_real(p)) return rc;
+  if (int rc = stage_acquire(p, 3)) return rc;
+  memcpy(p->h_stage, pos, 3 * sizeof(double));
+  if (int rc = h2d(p, p->scratch.p, p->h_stage, 3 * sizeof(double))) return rc;
+  if (int rc = stage_release(p)) return rc;
+  PlannerDev d = make_dev(p);
+  if (int rc = launch(p, set_initial_position_kernel, dim3((p->A + 127) / 128), dim3(128), 0, d,
+                      (const double *)p->scratch.p))
+    return rc;
+  p->fused_valid = false;
+  p->agents_touched = true;
+  return 0;
+}
+
+extern "C" int pmaf_set_real_position(pmaf_planner *p, const double pos[3]) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(pos != nullptr, PMAF_ERR_ARG, "pmaf_set_real_position: null position");
+  for (int i = 0; i < 3; ++i) p->h_real.pos[i] = pos[i];
+  p->real_path.insert(p->real_path.end(), pos, pos + 3);
+  return upload_real(p);
+}
+
+template <int LPA>
+static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, bool dynamic) {
+  const int groups = block / LPA;
+  const int grid = (p->A + groups - 1) / groups;
+  const size_t smem = rollout_smem_bytes(p->img, groups, p->known_words);
+  REQUIRE(smem <= 227 * 1024, PMAF_ERR_ARG, "rollout needs %zu B of shared memory (> 227 KB): too many obstacles",
+          smem);
+  auto kern = dynamic ? rollout_kernel<LPA, true> : rollout_kernel<LPA, false>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p->ctr.lanes_per_agent = LPA, p->ctr.block_threads = block, p->ctr.grid_blocks = grid, p->ctr.smem_bytes = (int)smem;
+  return launch(p, kern, dim3(grid), dim3(block), smem, d);
+}
+
+static void pick_rollout_shape(const pmaf_planner *p, int &lpa, int &block) {
+  lpa = p->tune_lpa ? p->tune_lpa : 32;
+  if (p->tune_block) {
+    block = p->tune_block;
+  } else {
+    // small populations are latency-bound: one warp per CTA spreads them over all 148 SMs;
+    // large ones pack 4 warps per CTA to amortise the obstacle staging
+    const long long warps = ((long long)p->A * lpa + 31) / 32;
+    block = warps <= 2 * 148 ? 32 : 128;
+  }
+  if (block < lpa) block = lpa;
+}
+
+static int launch_rollout(pmaf_planner *p) {
+  PlannerDev d = make_dev(p);
+  int lpa, block;
+  pick_rollout_shape(p, lpa, block);
+  CU(cudaMemsetAsync(p->step_counter.p, 0, sizeof(unsigned long long), p->stream));
+  p->roll_slot ^= 1;  // the slot used two rollouts ago: finished long before this point in the stream
+  if (int rc = harvest_timing(p, p->roll_slot, true)) return rc;
+  CU(cudaEventRecord(p->ev_roll[p->roll_slot][0], p->stream));
+  int rc;
+  const bool dyn = p->img.dynamic != 0;
+  switch (lpa) {
+    case 4: rc = launch_rollout_lpa<4>(p, d, block, dyn); break;
+    case 8: rc = launch_rollout_lpa<8>(p, d, block, dyn); break;
+    case 16: rc = launch_rollout_lpa<16>(p, d, block, dyn); break;
+    default: rc = launch_rollout_lpa<32>(p, d, block, dyn); break;
+  }
+  if (rc) return rc;
+  CU(cudaEventRecord(p->ev_roll[p->roll_slot][1], p->stream));
+  p->ctr.rollouts++;
+  p->rollout_pending = true, p->roll_timing[p->roll_slot] = true;
+  if (dyn) p->obstacles_advanced = true;
+  p->agents_touched = false;
+  return 0;
+}
+
+extern "C" int pmaf_start_prediction(pmaf_planner *p) {
+  ENTER(p);
+  NEED_INIT(p);
+  if (!p->agents_touched) return 0;  // every agent's stop condition already holds: nothing to run
+  REQUIRE(!(p->img.dynamic && p->obstacles_advanced), PMAF_ERR_STATE,
+          "pmaf_start_prediction: agents were repositioned without pmaf_reset_agents after a rollout over moving "
+          "obstacles; continuing from per-agent advanced obstacle copies is not supported");
+  if (int rc = finish_rollout(p)) return rc;
+  return launch_rollout(p);
+}
+
+extern "C" int pmaf_stop_prediction(pmaf_planner *p) {
+  ENTER(p);
+  return finish_rollout(p);
+}
+
+static bool same_cost(const CostParams &a, const CostParams &b) { return memcmp(&a, &b, sizeof a) == 0; }
+
+static int launch_evaluate(pmaf_planner *p, const CostParams &C) {
+  PlannerDev d = make_dev(p);
+  if (!(p->fused_valid && p->have_cost && same_cost(C, p->last_cost))) {
+    if (int rc = launch(p, workspace_cost_kernel, dim3((p->A + 127) / 128), dim3(128), 0, d, C)) return rc;
+  }
+  p->last_cost = C, p->have_cost = true;
+  const int threads = p->A >= 1024 ? 1024 : std::max(32, ((p->A + 31) / 32) * 32);
+  return launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, p->rec.p,
+                p->eval.p, 1);
+}
+
+static CostParams make_cost(double k_goal_dist, double k_path_len, double k_safe_dist, double k_workspace,
+                            const double ws[6]) {
+  CostParams C{};
+  C.k_goal_dist = k_goal_dist, C.k_path_len = k_path_len, C.k_safe_dist = k_safe_dist, C.k_workspace = k_workspace;
+  for (int i = 0; i < 6; ++i) C.ws[i] = ws[i];
+  return C;
+}
+
+extern "C" int pmaf_evaluate_agents(pmaf_planner *p, int n_obs, const double *obs_pos, const double *obs_vel,
+                                    const double *obs_rad, double k_goal_dist, double k_path_len,
+                                    double k_safe_dist, double k_workspace, const double ws_limits[6],
+                                    int *best_index) {
+  ENTER(p);
+  NEED_INIT(p);
+  (void)n_obs, (void)obs_pos, (void)obs_vel, (void)obs_rad;  // unused by the reference as well
+  REQUIRE(ws_limits && best_index, PMAF_ERR_ARG, "pmaf_evaluate_agents: null argument");
+  REQUIRE(p->world == 1, PMAF_ERR_STATE, "pmaf_evaluate_agents: sharded planners evaluate through pmaf_tick");
+  if (int rc = finish_rollout(p)) return rc;
+  const CostParams C = make_cost(k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits);
+  if (int rc = launch_evaluate(p, C)) return rc;
+  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult))) return rc;
+  if (int rc = d2h(p, &p->h_out->best, p->best.p, sizeof(DeviceBest))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  p->h_eval = p->h_out->eval, p->h_best = p->h_out->best;
+  *best_index = p->h_eval.best_index;
+  return 0;
+}
+
+// upload a live obstacle list unless it is byte-identical to the last one uploaded
+static int upload_live(pmaf_planner *p, int n_obs, const double *obs_pos, const double *obs_vel,
+                       const double *obs_rad) {
+  const size_t n = (size_t)n_obs;
+  std::vector<double> &last = p->h_live;
+  const bool same = p->upload_dedup && last.size() == 7 * n && memcmp(last.data(), obs_pos, 3 * n * sizeof(double)) == 0 &&
+                    memcmp(last.data() + 3 * n, obs_vel, 3 * n * sizeof(double)) == 0 &&
+                    memcmp(last.data() + 6 * n, obs_rad, n * sizeof(double)) == 0;
+  if (same) return 0;
+  last.resize(7 * n);
+  memcpy(last.data(), obs_pos, 3 * n * sizeof(double));
+  memcpy(last.data() + 3 * n, obs_vel, 3 * n * sizeof(double));
+  memcpy(last.data() + 6 * n, obs_rad, n * sizeof(double));
+  if (int rc = stage_acquire(p, 7 * n)) return rc;
+  memcpy(p->h_stage, last.data(), 7 * n * sizeof(double));
+  if (int rc = h2d(p, p->live_pos.p, p->h_stage, 3 * n * sizeof(double))) return rc;
+  if (int rc = h2d(p, p->live_vel.p, p->h_stage + 3 * n, 3 * n * sizeof(double))) return rc;
+  if (int rc = h2d(p, p->live_rad.p, p->h_stage + 6 * n, n * sizeof(double))) return rc;
+  return stage_release(p);
+}
+
+static int launch_real(pmaf_planner *p, int n_obs, double delta_t, int steps, int agent_id_global) {
+  PlannerDev d = make_dev(p);
+  RealArgs r{};
+  r.real = p->real.p, r.known = p->real_known.p, r.rot = p->real_rot.p, r.best = p->best.p;
+  r.best_random = p->best_random.p;
+  r.obs_pos = p->live_pos.p, r.obs_vel = p->live_vel.p, r.obs_rad = p->live_rad.p, r.n_obs = n_obs;
+  r.delta_t = delta_t, r.steps = steps, r.agent_id = agent_id_global, r.eval = p->eval.p;
+  r.path_out = p->real_path_out.p;
+  for (int i = 0; i < 3; ++i) r.goal[i] = p->goal[i];
+  return launch(p, real_agent_kernel, dim3(1), dim3(32), 0, d, r);
+}
+
+extern "C" int pmaf_move_real_agent(pmaf_planner *p, int n_obs, const double *obs_pos, const double *obs_vel,
+                                    const double *obs_rad, double delta_t, int steps, int agent_id) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(obs_pos && obs_vel && obs_rad, PMAF_ERR_ARG, "pmaf_move_real_agent: null obstacle array");
+  REQUIRE(n_obs >= 1 && n_obs <= p->O, PMAF_ERR_ARG,
+          "pmaf_move_real_agent: n_obs=%d but the planner was initialised with %d obstacles", n_obs, p->O);
+  REQUIRE(agent_id >= 0 && agent_id < p->n_global, PMAF_ERR_ARG, "pmaf_move_real_agent: agent_id=%d out of range",
+          agent_id);
+  REQUIRE(p->h_best.present, PMAF_ERR_STATE,
+          "pmaf_move_real_agent: no best agent yet (the reference dereferences a null best_agent_ here)");
+  REQUIRE(steps >= 0, PMAF_ERR_ARG, "pmaf_move_real_agent: steps=%d", steps);
+  if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+  for (int done = 0; done < steps;) {
+    const int chunk = std::min(steps - done, 256);
+    if (int rc = launch_real(p, n_obs, delta_t, chunk, agent_id)) return rc;
+    if (int rc = d2h(p, &p->h_out->real, p->real.p, sizeof(RealState))) return rc;
+    if (int rc = d2h(p, p->h_out->real_path, p->real_path_out.p, (size_t)chunk * 3 * sizeof(double))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    p->h_real = p->h_out->real;
+    p->real_path.insert(p->real_path.end(), p->h_out->real_path, p->h_out->real_path + (size_t)chunk * 3);
+    done += chunk;
+  }
+  return 0;
+}
+
+static int refresh_obstacle_copy(pmaf_planner *p, int n_obs, const double *obs_pos, const double *obs_vel,
+                                 const double *pos) {
+  memcpy(p->h_obs_pos.data(), obs_pos, (size_t)n_obs * 3 * sizeof(double));
+  memcpy(p->h_obs_vel.data(), obs_vel, (size_t)n_obs * 3 * sizeof(double));
+  const ObstacleImage im = layout_image(p->O, any_nonzero(p->h_obs_vel));
+  if (im.bytes != p->img.bytes) CU(p->image.resize(im.bytes));
+  p->img = im;
+  p->margin = broad_phase_margin(p, pos);
+  return 0;
+}
+
+extern "C" int pmaf_reset_agents(pmaf_planner *p, const double pos[3], const double vel[3], int n_obs,
+                                 const double *obs_pos, const double *obs_vel, const double *obs_rad) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(pos && vel && obs_pos && obs_vel && obs_rad, PMAF_ERR_ARG, "pmaf_reset_agents: null argument");
+  REQUIRE(n_obs >= 0 && n_obs <= p->O, PMAF_ERR_ARG,
+          "pmaf_reset_agents: n_obs=%d but the planner was initialised with %d obstacles (std::out_of_range in the "
+          "reference)", n_obs, p->O);
+  if (int rc = finish_rollout(p)) return rc;
+  if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+  if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, pos)) return rc;
+  if (int rc = stage_acquire(p, 6)) return rc;
+  memcpy(p->h_stage, pos, 3 * sizeof(double));
+  memcpy(p->h_stage + 3, vel, 3 * sizeof(double));
+  if (int rc = h2d(p, p->scratch.p, p->h_stage, 6 * sizeof(double))) return rc;
+  if (int rc = stage_release(p)) return rc;
+  p->fused_valid = p->have_cost;
+  if (int rc = launch_reset(p, true, false, p->scratch.p, n_obs, p->live_pos.p, p->live_vel.p, true, true))
+    return rc;
+  p->obstacles_advanced = false;
+  p->agents_touched = true;
+  return 0;
+}
+
+extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs, const double *obs_pos,
+                         const double *obs_vel, const double *obs_rad, double delta_t, double k_goal_dist,
+                         double k_path_len, double k_safe_dist, double k_workspace, const double ws_limits[6],
+                         int *best_index, double next_pos[3], double next_vel[3]) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(obs_pos && obs_vel && obs_rad && ws_limits, PMAF_ERR_ARG, "pmaf_tick: null argument");
+  REQUIRE(n_obs >= 1 && n_obs <= p->O, PMAF_ERR_ARG, "pmaf_tick: n_obs=%d (planner has %d obstacles)", n_obs, p->O);
+  REQUIRE(p->world == 1, PMAF_ERR_STATE, "pmaf_tick: sharded planners need an NCCL communicator");
+  if (measured_pos) {
+    if (int rc = pmaf_set_real_position(p, measured_pos)) return rc;
+  }
+  // the previous rollout is ordered before everything below by the stream; no host wait for it
+  if (int rc = harvest_timing(p, p->roll_slot, false)) return rc;
+  if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+  const CostParams C = make_cost(k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits);
+  if (int rc = launch_evaluate(p, C)) return rc;
+  if (int rc = launch_real(p, n_obs, delta_t, 1, -1)) return rc;
+  if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, p->h_real.pos)) return rc;
+  p->fused_valid = true;
+  if (int rc = launch_reset(p, true, true, nullptr, n_obs, p->live_pos.p, p->live_vel.p, true, true)) return rc;
+  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult))) return rc;
+  if (int rc = d2h(p, &p->h_out->best, p->best.p, sizeof(DeviceBest))) return rc;
+  if (int rc = d2h(p, &p->h_out->real, p->real.p, sizeof(RealState))) return rc;
+  CU(cudaEventRecord(p->ev_d2h, p->stream));
+  p->obstacles_advanced = false;
+  if (int rc = launch_rollout(p)) return rc;
+  CU(cudaEventSynchronize(p->ev_d2h));
+  p->h_eval = p->h_out->eval, p->h_best = p->h_out->best, p->h_real = p->h_out->real;
+  p->real_path.insert(p->real_path.end(), p->h_real.pos, p->h_real.pos + 3);
+  if (best_index) *best_index = p->h_eval.best_index;
+  for (int i = 0; i < 3; ++i) {
+    if (next_pos) next_pos[i] = p->h_real.pos[i];
+    if (next_vel) next_vel[i] = p->h_real.vel[i];
+  }
+  return 0;
+}
+
+// ---- getters ---------------------------------------------------------------------------------------------------------------
+extern "C" int pmaf_get_num_agents(pmaf_planner *p, int *n) {
+  ENTER(p);
+  REQUIRE(n, PMAF_ERR_ARG, "null output");
+  *n = p->A;
+  return 0;
+}
+#define VEC3_GETTER(name, src)                          \
+  extern "C" int name(pmaf_planner *p, double out[3]) { \
+    ENTER(p);                                           \
+    REQUIRE(out, PMAF_ERR_ARG, "null output");          \
+    for (int i = 0; i < 3; ++i) out[i] = (src)[i];      \
+    return 0;                                           \
+  }
+VEC3_GETTER(pmaf_get_next_position, p->h_real.pos)
+VEC3_GETTER(pmaf_get_next_velocity, p->h_real.vel)
+VEC3_GETTER(pmaf_get_ee_force, p->h_real.force)
+VEC3_GETTER(pmaf_get_goal_position, p->goal)
+VEC3_GETTER(pmaf_get_initial_position, p->mgr_init_pos)
+
+extern "C" int pmaf_get_dist_from_goal(pmaf_planner *p, double *out) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  *out = norm3(sub3(ld3(p->goal), ld3(p->h_real.pos)));  // cf_manager.h:87-89 on the host mirror
+  return 0;
+}
+extern "C" int pmaf_get_best_agent_type(pmaf_planner *p, int *out) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  *out = p->h_best.present ? p->h_best.type : -1;
+  return 0;
+}
+extern "C" int pmaf_get_best_agent_id(pmaf_planner *p, int *out) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  *out = p->h_best.present ? p->h_best.id : 0;
+  return 0;
+}
+
+static int fetch(pmaf_planner *p, void *dst, const void *src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream));
+  p->ctr.d2h_bytes += bytes;
+  return 0;
+}
+
+extern "C" int pmaf_get_num_prediction_steps(pmaf_planner *p, int agent, int *out) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(out && agent >= 0 && agent < p->A, PMAF_ERR_ARG, "pmaf_get_num_prediction_steps: agent=%d", agent);
+  if (int rc = finish_rollout(p)) return rc;
+  if (int rc = fetch(p, out, p->n_path.p + agent, sizeof(int))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+extern "C" int pmaf_get_real_num_prediction_steps(pmaf_planner *p, int *out) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  *out = (int)(p->real_path.size() / 3);
+  return 0;
+}
+
+extern "C" int pmaf_get_agent_summaries(pmaf_planner *p, int *steps, double *length, double *min_obs_dist,
+                                        int *reached, double *pred_time_ns, int *agent_type) {
+  ENTER(p);
+  NEED_INIT(p);
+  if (int rc = finish_rollout(p)) return rc;
+  const size_t A = p->A;
+  if (steps)
+    if (int rc = fetch(p, steps, p->n_path.p, A * sizeof(int))) return rc;
+  if (length)
+    if (int rc = fetch(p, length, p->path_len.p, A * sizeof(double))) return rc;
+  if (min_obs_dist)
+    if (int rc = fetch(p, min_obs_dist, p->min_obs.p, A * sizeof(double))) return rc;
+  if (reached)
+    if (int rc = fetch(p, reached, p->reached.p, A * sizeof(int))) return rc;
+  if (pred_time_ns)
+    if (int rc = fetch(p, pred_time_ns, p->pred_time.p, A * sizeof(double))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  if (agent_type)
+    for (size_t a = 0; a < A; ++a) agent_type[a] = agent_type_of_index(p->first_agent + (int)a);
+  return 0;
+}
+
+extern "C" int pmaf_get_predicted_paths(pmaf_planner *p, double *out, int stride) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(out && stride >= 1, PMAF_ERR_ARG, "pmaf_get_predicted_paths: bad argument");
+  if (int rc = finish_rollout(p)) return rc;
+  const size_t A = p->A, H = p->H;
+  std::vector<int> n(A);
+  std::vector<double> tmp(A * H * 3);
+  if (int rc = fetch(p, n.data(), p->n_path.p, A * sizeof(int))) return rc;
+  if (int rc = fetch(p, tmp.data(), p->paths.p, A * H * 3 * sizeof(double))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  for (size_t a = 0; a < A; ++a) {
+    const size_t rows = std::min<size_t>((size_t)n[a], (size_t)stride);
+    memcpy(out + a * (size_t)stride * 3, tmp.data() + a * H * 3, rows * 3 * sizeof(double));
+  }
+  return 0;
+}
+
+extern "C" int pmaf_get_predicted_path(pmaf_planner *p, int agent, double *out, int max_points, int *n_points) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(out && n_points && agent >= 0 && agent < p->A && max_points >= 0, PMAF_ERR_ARG,
+          "pmaf_get_predicted_path: bad argument");
+  if (int rc = finish_rollout(p)) return rc;
+  int n = 0;
+  if (int rc = fetch(p, &n, p->n_path.p + agent, sizeof(int))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  *n_points = n;
+  const size_t rows = (size_t)std::min(n, max_points);
+  if (rows) {
+    if (int rc = fetch(p, out, p->paths.p + (size_t)agent * p->H * 3, rows * 3 * sizeof(double))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+  }
+  return 0;
+}
+
+extern "C" int pmaf_get_agent_velocities(pmaf_planner *p, double *out) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  if (int rc = finish_rollout(p)) return rc;
+  if (int rc = fetch(p, out, p->vel.p, (size_t)p->A * 3 * sizeof(double))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+extern "C" int pmaf_get_planned_trajectory(pmaf_planner *p, double *out, int max_points, int *n_points) {
+  ENTER(p);
+  REQUIRE(n_points, PMAF_ERR_ARG, "null output");
+  const int n = (int)(p->real_path.size() / 3);
+  *n_points = n;
+  if (out && max_points > 0) memcpy(out, p->real_path.data(), (size_t)std::min(n, max_points) * 3 * sizeof(double));
+  return 0;
+}
+
+extern "C" int pmaf_get_obstacle_state(pmaf_planner *p, int n_obs, int *known, double *rot) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(n_obs == p->O, PMAF_ERR_ARG, "pmaf_get_obstacle_state: n_obs=%d, planner has %d", n_obs, p->O);
+  if (int rc = finish_rollout(p)) return rc;
+  const size_t A = p->A, O = p->O, KW = p->known_words;
+  if (known) {
+    std::vector<uint32_t> w(A * KW);
+    std::vector<unsigned char> rk(O);
+    if (int rc = fetch(p, w.data(), p->known.p, A * KW * sizeof(uint32_t))) return rc;
+    if (int rc = fetch(p, rk.data(), p->real_known.p, O)) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    for (size_t a = 0; a < A; ++a)
+      for (size_t i = 0; i < O; ++i) known[a * O + i] = (w[a * KW + (i >> 5)] >> (i & 31)) & 1u;
+    for (size_t i = 0; i < O; ++i) known[A * O + i] = rk[i] != 0;
+  }
+  if (rot) {
+    if (int rc = fetch(p, rot, p->rot.p, A * O * 3 * sizeof(double))) return rc;
+    if (int rc = fetch(p, rot + A * O * 3, p->real_rot.p, O * 3 * sizeof(double))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+  }
+  return 0;
+}
+
+extern "C" int pmaf_get_costs(pmaf_planner *p, double *costs) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(costs, PMAF_ERR_ARG, "null output");
+  if (int rc = fetch(p, costs, p->cost.p, (size_t)p->A * sizeof(double))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+extern "C" int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  if (p->initialized) {
+    if (int rc = finish_rollout(p)) return rc;
+    if (int rc = fetch(p, p->h_out->steps, p->step_counter.p, 2 * sizeof(unsigned long long))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    p->ctr.agent_steps = p->h_out->steps[0];
+    p->ctr.agent_steps_total = p->h_out->steps[1];
+  }
+  *out = p->ctr;
+  return 0;
+}
+
+extern "C" int pmaf_set_tuning(pmaf_planner *p, int lanes_per_agent, int block_threads) {
+  ENTER(p);
+  REQUIRE(lanes_per_agent == 0 || lanes_per_agent == 4 || lanes_per_agent == 8 || lanes_per_agent == 16 ||
+              lanes_per_agent == 32,
+          PMAF_ERR_ARG, "pmaf_set_tuning: lanes_per_agent must be 0, 4, 8, 16 or 32");
+  REQUIRE(block_threads == 0 || (block_threads >= 32 && block_threads <= 256 && block_threads % 32 == 0),
+          PMAF_ERR_ARG, "pmaf_set_tuning: block_threads must be 0 or a multiple of 32 in [32, 256]");
+  p->tune_lpa = lanes_per_agent, p->tune_block = block_threads;
+  return 0;
+}
+
+extern "C" int pmaf_set_upload_dedup(pmaf_planner *p, int dedup) {
+  ENTER(p);
+  p->upload_dedup = dedup != 0;
+  return 0;
+}
+
+extern "C" int pmaf_timer_start(pmaf_planner *p) {
+  ENTER(p);
+  CU(cudaEventRecord(p->ev_t0, p->stream));
+  return 0;
+}
+
+extern "C" int pmaf_timer_stop(pmaf_planner *p, double *elapsed_ms) {
+  ENTER(p);
+  REQUIRE(elapsed_ms, PMAF_ERR_ARG, "null output");
+  CU(cudaEventRecord(p->ev_t1, p->stream));
+  CU(cudaEventSynchronize(p->ev_t1));
+  if (p->rollout_pending) {
+    p->rollout_pending = false;  // the stream is idle now
+    if (int rc = harvest_timing(p, p->roll_slot ^ 1, true)) return rc;
+    if (int rc = harvest_timing(p, p->roll_slot, true)) return rc;
+  }
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, p->ev_t0, p->ev_t1));
+  *elapsed_ms = ms;
+  return 0;
+}
+
+extern "C" int pmaf_flush_l2(pmaf_planner *p) {
+  ENTER(p);
+  const size_t bytes = (size_t)256 << 20;
+  CU(p->l2_scratch.resize(bytes));
+  CU(cudaMemsetAsync(p->l2_scratch.p, 0x5a, bytes, p->stream));
+  return 0;
+}
+
+namespace pmaf {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3,
+         a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+}  // namespace pmaf
+
+extern "C" int pmaf_measure_fp64_peak(pmaf_planner *p, double *tflops) {
+  ENTER(p);
+  REQUIRE(tflops, PMAF_ERR_ARG, "null output");
+  const int blocks = 148 * 8, threads = 256, iters = 1 << 15;
+  DevBuf<double> out;
+  CU(out.resize((size_t)blocks * threads));
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(p->ev_t0, p->stream));
+    if (int rc = launch(p, fp64_peak_kernel, dim3(blocks), dim3(threads), 0, out.p, iters)) return rc;
+    CU(cudaEventRecord(p->ev_t1, p->stream));
+    CU(cudaEventSynchronize(p->ev_t1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, p->ev_t0, p->ev_t1));
+    if (rep > 0) best_ms = std::min(best_ms, ms);
+  }
+  out.release();
+  *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best_ms * 1e-3) / 1e12;
+  return 0;
+}

@@ -1,0 +1,369 @@
+// pmaf_kernels.cuh — sm_100a kernels of the multi-agent predictive rollout.
+//
+// Data-parallel decomposition: one GROUP of LPA lanes (4..32, a whole warp by
+// default) owns one agent for its whole horizon — the horizon is a strict recurrence, the agents
+// are independent (cf_manager.cpp:118-123). Inside a step the O(O) obstacle work is spread over
+// the group's lanes:
+//
+//   broad phase  (fp32, all O-1 field obstacles): conservative sphere test "may this obstacle be
+//                inside the detection shell?" against obstacle records staged in shared memory by
+//                one TMA bulk copy per CTA. An obstacle outside the shell is a strict no-op for the
+//                reference step (it cannot lower min_obs_dist_, which starts at the shell radius,
+//                adds a zero force, and is ignored by attractorForceScaling), so only candidates
+//                go on. Candidates are compacted, in obstacle order, into a per-group list.
+//   narrow phase (fp64, candidates only, one lane per candidate): the reference's circForce body
+//                (cf_agent.cpp:76-106) bit for bit; forces are then summed across lanes in
+//                obstacle-index order (serial fp64 adds on values fetched by warp shuffle) so that
+//                the sum has the reference's rounding; min distance and the closest obstacle are
+//                warp-shuffle reductions (exact: min / lexicographic min).
+//   scalar part  (gate, repulsion from the sentinel, attraction, integrator, cost accumulators):
+//                replicated in every lane of the group.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pmaf_math.cuh"
+
+namespace pmaf {
+
+constexpr int kMaxObstacles = 4096;  // candidate indices are uint16; the smem image must fit 227 KB
+
+// The step logic below (field_pass, agent_step) is written against a "group" policy so that the
+// SAME source runs on the GPU (Group<LPA>: sub-warp collectives) and, for CPU verification of the
+// operation order only, on the host (HostGroup: one lane, trivial collectives; used by
+// tests/host_step_check.cu, never by the product).
+#if defined(__CUDA_ARCH__)
+#define PMAF_FFS(x) __ffs(x)
+#define PMAF_POPC(x) __popc(x)
+#else
+#define PMAF_FFS(x) __builtin_ffs(x)
+#define PMAF_POPC(x) __builtin_popcount(x)
+#endif
+#define PMAF_HDT __host__ __device__ __forceinline__
+
+// Cost parameters of CfManager::evaluateAgents (cf_manager.cpp:293-297)
+struct CostParams {
+  double k_goal_dist, k_path_len, k_safe_dist, k_workspace;
+  double ws[6];
+};
+
+// Shared-memory image of the obstacle set, identical layout in the global staging buffer that the
+// CTA copies with one cp.async.bulk (offsets in bytes from the image base, all 16-byte aligned).
+struct ObstacleImage {
+  int n_obs;         // O, including the trailing sentinel
+  int dynamic;       // any obstacle velocity != 0: positions advance every step
+  uint32_t off_px, off_py, off_pz;  // double[O]  exact positions at the current rollout step
+  uint32_t off_rs;                  // double[O]  rad_ + obstacle radius (cf_agent.cpp:84)
+  uint32_t off_vx, off_vy, off_vz;  // double[O]  velocities           (dynamic only)
+  uint32_t off_dx, off_dy, off_dz;  // double[O]  velocity * dt        (dynamic only, :273)
+  uint32_t off_bp;                  // float4[O]  broad phase: x, y, z, (shell + rs + margin)^2
+  uint32_t bytes;                   // image size (multiple of 16)
+};
+
+struct DeviceBest {  // what RealCfAgent needs from *best_agent_ (cf_agent.cpp:368-387)
+  int present;       // best_agent_ != nullptr
+  int id;            // getAgentID() = global index + 1
+  int type;
+  int pad;
+};
+
+struct RealState {  // RealCfAgent scalar state (cf_agent.h:36-41)
+  double pos[3], vel[3], force[3], init_pos[3];
+};
+
+struct EvalResult {
+  int best_index;      // value returned by evaluateAgents (global index)
+  int argmin_index;    // serial argmin before hysteresis
+  int incumbent_changed;
+  int pad;
+  double best_cost, argmin_cost;
+};
+
+struct PlannerDev {  // kernel argument, passed by value
+  int n_agents;      // local agents
+  int first_agent;   // global index of local agent 0
+  int n_obs;
+  int max_steps;     // H: cap on path points (cf_agent.cpp:311)
+  double goal[3];
+  double shell, mass, rad, vel_max, approach_dist;
+  double pred_dt;    // prediction_freq_multiple * delta_t
+  // per-agent arrays [n_agents]
+  const double *k_attr, *k_circ, *k_repel, *k_damp;
+  double *init_pos;      // [A][3]
+  double *cur_pos;       // [A][3]  latest path point
+  double *vel;           // [A][3]
+  double *min_obs_dist;  // [A]
+  double *path_len;      // [A]   running getPathLength()
+  double *ws_cost;       // [A]   running workspace cost under fused_cost
+  double *pred_time_ns;  // [A]
+  int *n_path;           // [A]
+  int *reached;          // [A]
+  double *cost;          // [A]
+  double *paths;         // [A][H][3]
+  // per-(agent, obstacle)
+  double *rot;           // [A][O][3] field_rotation_vecs_
+  const double *random_vecs;  // [A][O][3] (RANDOM agents only)
+  uint32_t *known;       // [A][KW] bit i = known_obstacles_[i]
+  int known_words;       // KW = ceil(O / 32)
+  // obstacles
+  const unsigned char *image;  // staging image (global)
+  ObstacleImage img;
+  // fused cost accumulation
+  CostParams fused_cost;
+  int fused_valid;
+  // outputs
+  unsigned long long *step_counter;  // [0] executed integration steps of this rollout, [1] running total
+};
+
+// ---- small PTX wrappers (TMA bulk copy + mbarrier) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a bulk copy that never lands traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- group (sub-warp) collectives ------------------------------------------------------------------------
+template <int LPA>
+struct Group {
+  static constexpr int kLanes = LPA;
+  unsigned mask;  // lanes of this group inside the warp
+  int lane0;      // first lane of the group
+  int gl;         // lane index inside the group
+  int lane;       // lane index inside the warp
+  __device__ __forceinline__ Group() {
+    lane = threadIdx.x & 31;
+    gl = lane % LPA;
+    lane0 = lane - gl;
+    mask = LPA == 32 ? 0xffffffffu : (((1u << LPA) - 1u) << lane0);
+  }
+  __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(mask, p); }
+  __device__ __forceinline__ double bcast(double v, int src_lane) const { return __shfl_sync(mask, v, src_lane); }
+  __device__ __forceinline__ int bcast(int v, int src_lane) const { return __shfl_sync(mask, v, src_lane); }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ double min_reduce(double v) const {  // NaN never wins (a < b false)
+#pragma unroll
+    for (int off = LPA / 2; off > 0; off >>= 1) {
+      double o = __shfl_xor_sync(mask, v, off);
+      v = o < v ? o : v;
+    }
+    return v;
+  }
+  // lexicographic (value, index) minimum: smallest value, lowest index among equals
+  __device__ __forceinline__ void argmin_reduce(double &v, int &idx) const {
+#pragma unroll
+    for (int off = LPA / 2; off > 0; off >>= 1) {
+      double ov = __shfl_xor_sync(mask, v, off);
+      int oi = __shfl_xor_sync(mask, idx, off);
+      if (ov < v || (ov == v && oi < idx)) v = ov, idx = oi;
+    }
+  }
+};
+
+// single-lane stand-in with the same interface (host verification of the operation order)
+struct HostGroup {
+  static constexpr int kLanes = 1;
+  unsigned mask = 1u;
+  int lane0 = 0, gl = 0, lane = 0;
+  PMAF_HDT unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  PMAF_HDT double bcast(double v, int) const { return v; }
+  PMAF_HDT int bcast(int v, int) const { return v; }
+  PMAF_HDT void sync() const {}
+  PMAF_HDT double min_reduce(double v) const { return v; }
+  PMAF_HDT void argmin_reduce(double &, int &) const {}
+};
+
+// ---- obstacle accessors ---------------------------------------------------------------------------------
+struct SmemObstacles {  // rollout: the CTA's shared-memory image
+  const double *px, *py, *pz, *rs, *vx, *vy, *vz;
+  bool dynamic;
+  PMAF_HDT v3 pos(int i) const { return mk3(px[i], py[i], pz[i]); }
+  PMAF_HDT v3 vel(int i) const { return dynamic ? mk3(vx[i], vy[i], vz[i]) : mk3(0.0, 0.0, 0.0); }
+  PMAF_HDT double rsum(int i) const { return rs[i]; }
+};
+struct LiveObstacles {  // real agent: the live list passed to moveRealEEAgent, in global memory
+  const double *p, *v, *r;
+  double agent_rad;
+  PMAF_HDT v3 pos(int i) const { return ld3(p + 3 * i); }
+  PMAF_HDT v3 vel(int i) const { return ld3(v + 3 * i); }
+  PMAF_HDT double rsum(int i) const { return agent_rad + r[i]; }
+};
+
+// known_obstacles_ accessors
+struct KnownBits {  // bit mask in shared memory (one row per group)
+  uint32_t *w;
+  PMAF_HDT bool test(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+  PMAF_HDT void set(int i) const {
+#if defined(__CUDA_ARCH__)
+    atomicOr(&w[i >> 5], 1u << (i & 31));  // lanes of a group may share a word
+#else
+    w[i >> 5] |= 1u << (i & 31);
+#endif
+  }
+};
+struct KnownBytes {  // the real agent's flags in global memory
+  unsigned char *b;
+  PMAF_HDT bool test(int i) const { return b[i] != 0; }
+  PMAF_HDT void set(int i) const { b[i] = 1; }
+};
+
+// nearest other field obstacle to obstacle `id` (cf_agent.cpp:434-446): serial scan semantics —
+// strict '>' from index 0, start value 100.0, default index 0 — evaluated cooperatively.
+#pragma nv_exec_check_disable
+template <class G, class Obs>
+PMAF_HDT int nearest_other_obstacle(const G &g, const Obs &obs, int n_field, int id) {
+  constexpr int LPA = G::kLanes;
+  v3 oi = obs.pos(id);
+  double best = 100.0;
+  int best_i = 0x7fffffff;
+  for (int i = g.gl; i < n_field; i += LPA) {
+    if (i != id) {
+      double d = norm3(sub3(oi, obs.pos(i)));
+      if (best > d) best = d, best_i = i;
+    }
+  }
+  g.argmin_reduce(best, best_i);
+  return best_i == 0x7fffffff ? 0 : best_i;
+}
+
+// CfAgent::circForce / RealCfAgent::circForce (cf_agent.cpp:72-144) over a candidate list, plus the
+// closest-obstacle search of attractorForceScaling (:199-211).
+//   cand == nullptr: candidates are 0..n_cand-1 themselves.
+//   outputs (identical in every lane of the group): force = sum of curr_force in obstacle order,
+//   min_d = min over non-skipped candidates of dist_obs (+inf if none),
+//   closest_d / closest_i = first obstacle with the smallest dist_obs < shell (closest_i < 0 if none).
+#pragma nv_exec_check_disable
+template <class G, class Obs, class Known>
+PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t *cand, int n_cand, int type, v3 p,
+                         v3 v, v3 goal, double shell, double k_circ, const Known &known, double *rot_row,
+                         const double *random_row, v3 &force, double &min_d, double &closest_d, int &closest_i) {
+  constexpr int LPA = G::kLanes;
+  const v3 goal_vec = sub3(goal, p);
+  const v3 ghat = normalized3(goal_vec);
+  const bool needs_nn = type == OBSTACLE_HEURISTIC || type == GOAL_OBSTACLE_HEURISTIC;
+  force = mk3(0.0, 0.0, 0.0);
+  double lmin = (double)INFINITY;
+  double lcd = shell;
+  int lci = 0x7fffffff;
+
+  for (int c0 = 0; c0 < n_cand; c0 += LPA) {
+    const int c = c0 + g.gl;
+    const bool active = c < n_cand;
+    const int i = active ? (cand ? (int)cand[c] : c) : 0;
+    bool in_shell = false, first_seen = false;
+    v3 to_obs = mk3(0.0, 0.0, 0.0), rel = mk3(0.0, 0.0, 0.0), oi = mk3(0.0, 0.0, 0.0);
+    double dist_obs = 0.0;
+    if (active) {
+      oi = obs.pos(i);
+      const v3 rov = sub3(oi, p);
+      rel = sub3(v, obs.vel(i));
+      const double z = dot3(rov, rov);
+      const double n = sqrt(z);
+      to_obs = normalized_zn(rov, z, n);
+      const double d = clamp_dist(n - obs.rsum(i));
+      // attractorForceScaling's search ignores the skip test (:201-211)
+      if (d < lcd) lcd = d, lci = i;
+      const bool skip = dot3(to_obs, ghat) < -0.01 && dot3(rov, rel) < -0.01;  // :79-82
+      if (!skip) {
+        if (d < lmin) lmin = d;  // :86-88
+        dist_obs = d;
+        in_shell = d < shell;  // :91
+        first_seen = in_shell && !known.test(i);
+      }
+    }
+    int nn = 0;
+    if (needs_nn) {  // group-uniform branch: cooperative nearest-neighbour scans, one per new obstacle
+      unsigned m = g.ballot(first_seen);
+      while (m) {
+        const int src = PMAF_FFS(m) - 1;
+        m &= m - 1;
+        const int id = g.bcast(i, src);
+        const int r = nearest_other_obstacle(g, obs, n_field, id);
+        if (g.lane == src) nn = r;
+      }
+    }
+    v3 f = mk3(0.0, 0.0, 0.0);
+    bool contributes = false;
+    if (in_shell) {
+      v3 rot_i;
+      if (first_seen) {  // :92-96
+        switch (type) {
+          case HAD_HEURISTIC: rot_i = rot_had(p, goal, oi); break;
+          case RANDOM_AGENT: rot_i = rot_random(p, goal, ld3(random_row + 3 * i)); break;
+          case OBSTACLE_HEURISTIC:
+            rot_i = n_field + 1 < 2 ? mk3(0.0, 0.0, 1.0) : rot_obstacle(to_obs, oi, obs.pos(nn));
+            break;
+          case GOAL_OBSTACLE_HEURISTIC: rot_i = rot_goal_obstacle(p, goal, to_obs, oi, obs.pos(nn)); break;
+          default: rot_i = mk3(0.0, 0.0, 1.0); break;  // GOAL :408-412, VEL :539-543
+        }
+        st3(rot_row + 3 * i, rot_i);
+        known.set(i);
+      } else {
+        rot_i = ld3(rot_row + 3 * i);
+      }
+      const double zr = dot3(rel, rel);
+      const double vel_norm = sqrt(zr);
+      if (vel_norm != 0) {  // :98
+        const v3 nv = div3(rel, vel_norm);
+        const v3 nv_eigen = zr > 0.0 ? nv : rel;
+        const v3 current = current_vector(type, p, goal, to_obs, nv_eigen, rot_i);
+        f = circ_force_term(k_circ, dist_obs, nv, current);
+        contributes = true;
+      }
+    }
+    // force_ += curr_force in obstacle order (:106): candidates are sorted, lanes are in list order
+    unsigned fm = g.ballot(contributes);
+    while (fm) {
+      const int src = PMAF_FFS(fm) - 1;
+      fm &= fm - 1;
+      force.x += g.bcast(f.x, src);
+      force.y += g.bcast(f.y, src);
+      force.z += g.bcast(f.z, src);
+    }
+  }
+  min_d = g.min_reduce(lmin);
+  g.argmin_reduce(lcd, lci);
+  closest_d = lcd;
+  closest_i = lci == 0x7fffffff ? -1 : lci;
+}
+
+// One step of cfPrediction's loop body (cf_agent.cpp:312-326) given the field pass results.
+struct StepGains {
+  double k_attr, k_circ, k_repel, k_damp;
+};
+
+}  // namespace pmaf

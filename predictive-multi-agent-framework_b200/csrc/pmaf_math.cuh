@@ -1,0 +1,235 @@
+// pmaf_math.cuh — binary64 building blocks of the circular-field agent step, in the operation
+// order of the reference (citations: /root/reference/src/bimanual_planning_ros/src/cf_agent.cpp
+// unless noted). Every function is __host__ __device__ so that the same source can be checked on
+// the CPU (tests/host_math_check.cpp) and runs inside the sm_100a kernels.
+//
+// Exactness contract: compile with -fmad=false (device) / -ffp-contract=off (host). The
+// reference is built for default x86-64 (no FMA), Eigen 3.3 fixed-size vectors:
+//   dot / squaredNorm reduce as (x0*y0 + x1*y1) + x2*y2, norm = sqrt(squaredNorm),
+//   normalized(): z = squaredNorm; z > 0 ? v / sqrt(z) : v   (true divisions),
+//   cross(): (a1 b2 - a2 b1, a2 b0 - a0 b2, a0 b1 - a1 b0).
+// Division and sqrt are IEEE correctly rounded on both sides (nvcc default -prec-div/-prec-sqrt).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PMAF_HD __host__ __device__ __forceinline__
+#else
+#define PMAF_HD inline
+#endif
+
+namespace pmaf {
+
+// CfAgent::Type, cf_agent.h:59-68
+enum AgentType : int {
+  REAL_AGENT = 0,
+  GOAL_HEURISTIC = 1,
+  OBSTACLE_HEURISTIC = 2,
+  GOAL_OBSTACLE_HEURISTIC = 3,
+  VEL_HEURISTIC = 4,
+  RANDOM_AGENT = 5,
+  HAD_HEURISTIC = 6,
+  UNDEFINED_AGENT = 7
+};
+
+// type of the agent at GLOBAL index idx, CfManager::init cf_manager.cpp:70-104
+PMAF_HD int agent_type_of_index(int idx) {
+  switch (idx) {
+    case 0: return HAD_HEURISTIC;
+    case 1: return GOAL_HEURISTIC;
+    case 2: return OBSTACLE_HEURISTIC;
+    case 3: return GOAL_OBSTACLE_HEURISTIC;
+    case 4: return VEL_HEURISTIC;
+    default: return RANDOM_AGENT;
+  }
+}
+
+struct v3 {
+  double x, y, z;
+};
+
+PMAF_HD v3 mk3(double x, double y, double z) {
+  v3 r;
+  r.x = x, r.y = y, r.z = z;
+  return r;
+}
+PMAF_HD v3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
+PMAF_HD void st3(double *p, v3 a) { p[0] = a.x, p[1] = a.y, p[2] = a.z; }
+PMAF_HD v3 add3(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PMAF_HD v3 sub3(v3 a, v3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PMAF_HD v3 mul3(v3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
+PMAF_HD v3 div3(v3 a, double s) { return mk3(a.x / s, a.y / s, a.z / s); }
+PMAF_HD double dot3(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+PMAF_HD double norm3(v3 a) { return sqrt(dot3(a, a)); }
+PMAF_HD v3 cross3(v3 a, v3 b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// Eigen normalized(): given z = squaredNorm and n = sqrt(z) already computed
+PMAF_HD v3 normalized_zn(v3 a, double z, double n) { return z > 0.0 ? div3(a, n) : a; }
+PMAF_HD v3 normalized3(v3 a) {
+  double z = dot3(a, a);
+  return z > 0.0 ? div3(a, sqrt(z)) : a;
+}
+// std::max(d, 1e-5) (cf_agent.cpp:85): NaN stays NaN
+PMAF_HD double clamp_dist(double d) { return d < 1e-5 ? 1e-5 : d; }
+
+// ---- rotation vectors (calculateRotationVector) ------------------------------------------------
+// to_obs = normalized(o_i - p), the same value circForce already formed for its skip test.
+
+// HAD :599-611 — NaN when d is parallel to the goal vector
+PMAF_HD v3 rot_had(v3 p, v3 goal, v3 o_i) {
+  v3 goal_vec = sub3(goal, p);
+  v3 rob_obs = sub3(o_i, p);
+  double gn = norm3(goal_vec);
+  double s = dot3(rob_obs, goal_vec) / (gn * gn);
+  v3 d = sub3(add3(p, mul3(goal_vec, s)), o_i);
+  v3 c = cross3(d, goal_vec);
+  return div3(c, norm3(c));
+}
+// RANDOM :559-566 — not normalised
+PMAF_HD v3 rot_random(v3 p, v3 goal, v3 random_i) { return cross3(normalized3(sub3(goal, p)), random_i); }
+// OBSTACLE :447-460, o_c = position of the obstacle closest to obstacle i (:434-446)
+PMAF_HD v3 rot_obstacle(v3 to_obs, v3 o_i, v3 o_c) {
+  v3 obstacle_vec = sub3(o_c, o_i);
+  v3 current = sub3(mul3(to_obs, dot3(obstacle_vec, to_obs)), obstacle_vec);
+  return normalized3(cross3(current, to_obs));
+}
+// GOAL_OBSTACLE :493-517
+PMAF_HD v3 rot_goal_obstacle(v3 p, v3 goal, v3 to_obs, v3 o_i, v3 o_c) {
+  v3 obstacle_vec = sub3(o_c, o_i);
+  v3 obst_current = sub3(mul3(to_obs, dot3(obstacle_vec, to_obs)), obstacle_vec);
+  v3 goal_vec = sub3(goal, p);
+  v3 goal_current = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+  v3 current = add3(normalized3(goal_current), normalized3(obst_current));
+  if (norm3(current) < 1e-10) current = mk3(0.0, 0.0, 1.0);
+  current = normalized3(current);
+  return normalized3(cross3(current, to_obs));
+}
+
+// ---- current vectors (currentVector) -------------------------------------------------------------
+// rel = relative velocity (the caller passes rel_vel as agent_vel, :100), nv_eigen = rel.normalized()
+PMAF_HD v3 current_vector(int type, v3 p, v3 goal, v3 to_obs, v3 nv_eigen, v3 rot_i) {
+  if (type == GOAL_HEURISTIC) {  // :389-406
+    v3 goal_vec = sub3(goal, p);
+    v3 current = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+    if (norm3(current) < 1e-10) current = mk3(0.0, 0.0, 1.0);
+    return normalized3(current);
+  }
+  if (type == VEL_HEURISTIC) {  // :520-537
+    v3 current = sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs)));
+    if (norm3(current) < 1e-10) current = mk3(0.0, 0.0, 1.0);
+    return normalized3(current);
+  }
+  // OBSTACLE :414-426, GOAL_OBSTACLE :463-475, RANDOM :545-557, HAD :585-597
+  return normalized3(cross3(to_obs, rot_i));
+}
+
+// circular-field force of one in-shell obstacle, :98-104
+PMAF_HD v3 circ_force_term(double k_circ, double dist_obs, v3 nv, v3 current) {
+  return mul3(cross3(nv, cross3(current, nv)), k_circ / (dist_obs * dist_obs));
+}
+
+// ---- scalar parts of one step ----------------------------------------------------------------------
+// gate of cfPlanner / cfPrediction, :287-289 / :315-317 / :352-354
+PMAF_HD bool field_gate_open(double dist_goal, v3 p, v3 v, v3 init_pos, double approach_dist, double vel_max) {
+  return !(dist_goal < approach_dist || (norm3(v) < 0.5 * vel_max && norm3(sub3(p, init_pos)) < 0.2));
+}
+
+// repelForce :159-181 on the sentinel (last obstacle); rsum = rad_ + sentinel radius.
+PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, double rsum, double shell, double k_repel) {
+  v3 dv = sub3(p, o_s);
+  double z = dot3(dv, dv);
+  double n = sqrt(z);
+  double d = clamp_dist(n - rsum);
+  v3 repel = mk3(0.0, 0.0, 0.0);
+  if (d < shell) {
+    v3 u = normalized_zn(dv, z, n);
+    double s1 = 1.0 / d - 1.0 / shell;
+    double s2 = d * d;
+    repel = mk3(k_repel * u.x * s1 / s2, k_repel * u.y * s1 / s2, k_repel * u.z * s1 / s2);
+  }
+  v3 total = add3(mk3(0.0, 0.0, 0.0), repel);  // total_repel_force += repel_force (:179)
+  return add3(force, total);
+}
+
+// attractorForce :183-193
+PMAF_HD v3 add_attractor_force(v3 force, v3 goal_vec, v3 v, double k_attr, double k_damp, double k_goal_scale,
+                               double vel_max) {
+  if (k_attr == 0.0) return force;
+  v3 vel_des = mul3(goal_vec, k_attr / k_damp);
+  double lim = vel_max / norm3(vel_des);
+  double scale_lim = lim < 1.0 ? lim : 1.0;  // std::min(1.0, lim)
+  vel_des = mul3(vel_des, scale_lim);
+  return add3(force, mul3(sub3(vel_des, v), k_goal_scale * k_damp));
+}
+
+// tail of attractorForceScaling :212-226 once the closest in-shell obstacle (distance
+// closest_d, position o_c) is known
+PMAF_HD double attractor_scaling(v3 goal_vec, v3 p, v3 v, double vel_max, double shell, double closest_d, v3 o_c) {
+  if (dot3(goal_vec, v) <= 0.0 && norm3(v) < vel_max - 0.1 * vel_max && norm3(goal_vec) > 0.15) return 0.0;
+  double w1 = 1 - exp(-sqrt(closest_d) / shell);
+  v3 rov = sub3(o_c, p);
+  double w2 = 1 - (dot3(goal_vec, rov) / (norm3(goal_vec) * norm3(rov)));
+  w2 = w2 * w2;
+  return w1 * w2;
+}
+
+// updatePositionAndVelocity :253-268
+PMAF_HD void integrate_step(v3 force, double mass, double dt, double vel_max, v3 &p, v3 &v) {
+  v3 acc = div3(force, mass);
+  double acc_norm = norm3(acc);
+  if (acc_norm > 13.0) acc = mul3(acc, 13.0 / acc_norm);
+  v3 np = mk3((p.x + 0.5 * acc.x * dt * dt) + v.x * dt, (p.y + 0.5 * acc.y * dt * dt) + v.y * dt,
+              (p.z + 0.5 * acc.z * dt * dt) + v.z * dt);
+  v = add3(v, mul3(acc, dt));
+  double vel_norm = norm3(v);
+  if (vel_norm > vel_max) v = mul3(v, vel_max / vel_norm);
+  p = np;
+}
+
+// CfAgent::setVelocity :54-61
+PMAF_HD v3 clamp_velocity(v3 v, double vel_max) {
+  double n = norm3(v);
+  return n > vel_max ? mul3(v, vel_max / n) : v;
+}
+
+// workspace term of one path point, CfManager::evaluateAgents cf_manager.cpp:302-323
+// ws = [x+, x-, y+, y-, z+, z-]
+PMAF_HD double add_workspace_cost(double cost, v3 q, const double *ws, double k_workspace) {
+  double t;
+  if (q.x > ws[0]) {
+    t = fabs(q.x - ws[0]) * k_workspace;
+    cost += t * t;
+  } else if (q.x < ws[1]) {
+    t = fabs(q.x - ws[1]) * k_workspace;
+    cost += t * t;
+  }
+  if (q.y > ws[2]) {
+    t = fabs(q.y - ws[2]) * k_workspace;
+    cost += t * t;
+  } else if (q.y < ws[3]) {
+    t = fabs(q.y - ws[3]) * k_workspace;
+    cost += t * t;
+  }
+  if (q.z > ws[4]) {
+    t = fabs(q.z - ws[4]) * k_workspace;
+    cost += t * t;
+  } else if (q.z < ws[5]) {
+    t = fabs(q.z - ws[5]) * k_workspace;
+    cost += t * t;
+  }
+  return cost;
+}
+
+// remaining terms of the per-agent cost, cf_manager.cpp:324-333
+PMAF_HD double finish_cost(double ws_cost, double goal_dist, double approach_dist, double k_goal_dist,
+                           double path_len, double k_path_len, double k_safe_dist, double min_obs_dist) {
+  double cost = ws_cost;
+  if (goal_dist > approach_dist) cost += goal_dist * k_goal_dist;
+  cost += path_len * k_path_len;
+  cost += k_safe_dist / min_obs_dist;
+  if (min_obs_dist < 2e-5) cost += 10000.0;
+  return cost;
+}
+
+}  // namespace pmaf

@@ -1,0 +1,488 @@
+// pmaf_rollout.cuh — the rollout kernel (CfAgent::cfPrediction, cf_agent.cpp:302-341, for every
+// agent at once) and the small per-tick kernels around it.
+#pragma once
+#include "pmaf_kernels.cuh"
+
+namespace pmaf {
+
+// Shared memory of a rollout CTA:
+//   [0, 16)                      mbarrier
+//   [16, 16 + img.bytes)         obstacle image (TMA bulk copy of PlannerDev::image)
+//   then per group: uint16 cand[cand_stride], uint32 known[known_words]
+__host__ __device__ inline uint32_t rollout_cand_stride(int n_obs) { return (uint32_t)((n_obs + 7) & ~7); }
+__host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, int groups, int known_words) {
+  size_t b = 16 + img.bytes;
+  b += (size_t)groups * rollout_cand_stride(img.n_obs) * sizeof(uint16_t);
+  b += (size_t)groups * known_words * sizeof(uint32_t);
+  return (b + 15) & ~(size_t)15;
+}
+
+// One integration step of one agent (loop body of cfPrediction, cf_agent.cpp:312-326).
+// Returns the new position in p / velocity in v; updates min_obs.
+#pragma nv_exec_check_disable
+template <class G>
+PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
+                         const KnownBits &known, int type, const StepGains &k, v3 init_pos, double *rot_row,
+                         const double *random_row, double dist_goal, v3 &p, v3 &v, double &min_obs) {
+  constexpr int LPA = G::kLanes;
+  const v3 goal = ld3(P.goal);
+  const int n_field = P.n_obs - 1;  // the sentinel is excluded from the field loops (:75)
+  v3 force = mk3(0.0, 0.0, 0.0);    // resetForce()
+  double k_goal_scale = 1.0;
+  if (field_gate_open(dist_goal, p, v, init_pos, P.approach_dist, P.vel_max)) {
+    // ---- broad phase: fp32 sphere test, ordered compaction of candidate indices ----
+    const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
+    const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
+    int n_cand = 0;
+    for (int base = 0; base < n_field; base += LPA) {
+      const int i = base + g.gl;
+      bool c = false;
+      if (i < n_field) {
+        const float4 b = bp[i];
+        const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
+        c = dx * dx + dy * dy + dz * dz < b.w;
+      }
+      const unsigned m = g.ballot(c);
+      if (c) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
+      n_cand += PMAF_POPC(m);
+    }
+    g.sync();
+    // ---- narrow phase ----
+    double min_d, closest_d;
+    int closest_i;
+    field_pass(g, obs, n_field, cand, n_cand, type, p, v, goal, P.shell, k.k_circ, known, rot_row,
+                    random_row, force, min_d, closest_d, closest_i);
+    if (min_d < min_obs) min_obs = min_d;
+    if (norm3(force) > 1e-5) {  // :319-321
+      k_goal_scale = closest_i < 0 ? 1.0
+                                   : attractor_scaling(sub3(goal, p), p, v, P.vel_max, P.shell, closest_d,
+                                                       obs.pos(closest_i));
+    }
+    g.sync();  // cand[] is rewritten by the next step's broad phase
+  }
+  const int s = P.n_obs - 1;
+  force = add_repel_force(force, p, obs.pos(s), obs.rsum(s), P.shell, k.k_repel);
+  force = add_attractor_force(force, sub3(goal, p), v, k.k_attr, k.k_damp, k_goal_scale, P.vel_max);
+  integrate_step(force, P.mass, P.pred_dt, P.vel_max, p, v);
+}
+
+// Rollout of every agent to termination. Each group continues ITS agent from the agent's current
+// state (latest path point, velocity, min_obs_dist, known flags, path length, workspace cost) —
+// which resetEEAgents made uniform in the normal tick order — so any call order of the reference
+// API keeps its meaning; an already terminated agent executes zero steps.
+template <int LPA, bool DYNAMIC>
+__global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+  unsigned char *img = smem + 16;
+  const int groups = blockDim.x / LPA;
+  uint16_t *cand_all = reinterpret_cast<uint16_t *>(img + P.img.bytes);
+  const uint32_t cand_stride = rollout_cand_stride(P.n_obs);
+  uint32_t *known_all = reinterpret_cast<uint32_t *>(cand_all + (size_t)groups * cand_stride);
+
+  // stage the obstacle set: one TMA bulk copy per CTA, completion on an mbarrier
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, P.img.bytes);
+    tma_bulk_g2s(img, P.image, P.img.bytes, bar);
+  }
+
+  const Group<LPA> g;
+  const int group_in_block = threadIdx.x / LPA;
+  const int a = blockIdx.x * groups + group_in_block;  // local agent index
+  const bool have_agent = a < P.n_agents;
+  uint16_t *cand = cand_all + (size_t)group_in_block * cand_stride;
+  KnownBits known;
+  known.w = known_all + (size_t)group_in_block * P.known_words;
+
+  // per-agent state (overlaps the bulk copy)
+  v3 p = mk3(0, 0, 0), v = p, init_pos = p;
+  double min_obs = 0, path_len = 0, ws_cost = 0;
+  int n_path = 0, type = 0;
+  StepGains k = {0, 0, 0, 0};
+  double *rot_row = nullptr;
+  const double *random_row = nullptr;
+  if (have_agent) {
+    p = ld3(P.cur_pos + 3 * a);
+    v = ld3(P.vel + 3 * a);
+    init_pos = ld3(P.init_pos + 3 * a);
+    min_obs = P.min_obs_dist[a];
+    path_len = P.path_len[a];
+    ws_cost = P.ws_cost[a];
+    n_path = P.n_path[a];
+    type = agent_type_of_index(P.first_agent + a);
+    const int ga = P.first_agent + a;  // gains are indexed by GLOBAL agent index
+    k.k_attr = P.k_attr[ga], k.k_circ = P.k_circ[ga], k.k_repel = P.k_repel[ga], k.k_damp = P.k_damp[ga];
+    rot_row = P.rot + (size_t)a * P.n_obs * 3;
+    random_row = P.random_vecs + (size_t)a * P.n_obs * 3;
+    for (int w = g.gl; w < P.known_words; w += LPA) known.w[w] = P.known[(size_t)a * P.known_words + w];
+  }
+  g.sync();
+  mbar_wait(bar, 0);
+
+  SmemObstacles obs;
+  obs.px = reinterpret_cast<const double *>(img + P.img.off_px);
+  obs.py = reinterpret_cast<const double *>(img + P.img.off_py);
+  obs.pz = reinterpret_cast<const double *>(img + P.img.off_pz);
+  obs.rs = reinterpret_cast<const double *>(img + P.img.off_rs);
+  obs.vx = reinterpret_cast<const double *>(img + P.img.off_vx);
+  obs.vy = reinterpret_cast<const double *>(img + P.img.off_vy);
+  obs.vz = reinterpret_cast<const double *>(img + P.img.off_vz);
+  obs.dynamic = DYNAMIC;
+  const float4 *bp = reinterpret_cast<const float4 *>(img + P.img.off_bp);
+
+  const v3 goal = ld3(P.goal);
+  const unsigned long long t0 = global_timer_ns();
+  int steps_run = 0;
+  bool alive = have_agent;
+  double *path_row = have_agent ? P.paths + (size_t)a * P.max_steps * 3 : nullptr;
+
+  for (;;) {
+    if (alive) {
+      const double dist_goal = norm3(sub3(goal, p));
+      if (dist_goal > 0.1 && n_path < P.max_steps) {  // :310-311
+        const v3 prev = p;
+        agent_step(g, P, obs, bp, cand, known, type, k, init_pos, rot_row, random_row, dist_goal, p, v,
+                        min_obs);
+        path_len += norm3(sub3(p, prev));  // getPathLength term (:29)
+        if (P.fused_valid) ws_cost = add_workspace_cost(ws_cost, p, P.fused_cost.ws, P.fused_cost.k_workspace);
+        if (g.gl == 0) st3(path_row + (size_t)n_path * 3, p);
+        ++n_path;
+        ++steps_run;
+      } else {
+        alive = false;
+      }
+    }
+    if (DYNAMIC) {
+      // predictObstacles (:270-276): every private obstacle copy advances identically, so the CTA
+      // keeps ONE copy and steps it in lockstep with its agents
+      if (!__syncthreads_or(alive)) break;
+      double *px = const_cast<double *>(obs.px), *py = const_cast<double *>(obs.py),
+             *pz = const_cast<double *>(obs.pz);
+      const double *dx = reinterpret_cast<const double *>(img + P.img.off_dx);
+      const double *dy = reinterpret_cast<const double *>(img + P.img.off_dy);
+      const double *dz = reinterpret_cast<const double *>(img + P.img.off_dz);
+      float4 *bpw = const_cast<float4 *>(bp);
+      for (int i = threadIdx.x; i < P.n_obs; i += blockDim.x) {
+        const double x = px[i] + dx[i], y = py[i] + dy[i], z = pz[i] + dz[i];
+        px[i] = x, py[i] = y, pz[i] = z;
+        float4 b = bpw[i];
+        b.x = (float)x, b.y = (float)y, b.z = (float)z;
+        bpw[i] = b;
+      }
+      __syncthreads();
+    } else if (!alive) {
+      break;
+    }
+  }
+
+  if (have_agent) {
+    for (int w = g.gl; w < P.known_words; w += LPA) P.known[(size_t)a * P.known_words + w] = known.w[w];
+    if (g.gl == 0) {
+      st3(P.cur_pos + 3 * a, p);
+      st3(P.vel + 3 * a, v);
+      P.min_obs_dist[a] = min_obs;
+      P.path_len[a] = path_len;
+      P.ws_cost[a] = ws_cost;
+      P.n_path[a] = n_path;
+      if (steps_run > 0) {  // `if (running_)`, :330-337
+        P.pred_time_ns[a] = (double)(global_timer_ns() - t0);
+        P.reached[a] = norm3(sub3(goal, p)) < 0.100001 ? 1 : 0;
+        atomicAdd(P.step_counter, (unsigned long long)steps_run);
+        atomicAdd(P.step_counter + 1, (unsigned long long)steps_run);
+      }
+    }
+  }
+}
+
+// broad-phase record of one obstacle: fp32 centre and squared candidate radius
+PMAF_HDT float4 broad_phase_record(v3 pos, double shell, double rsum, float margin) {
+  const float thr = (float)(shell + rsum) + margin;
+  float4 r;
+  r.x = (float)pos.x, r.y = (float)pos.y, r.z = (float)pos.z, r.w = thr * thr;
+  return r;
+}
+
+// ---- resetEEAgents (cf_manager.cpp:246-255) + obstacle staging -------------------------------------------
+struct ResetArgs {
+  const double *pos_vel;      // [6] position, velocity handed to resetEEAgents (device copy), or
+  const RealState *real;      // ... the real agent's state when from_real != 0 (fused tick)
+  int from_real;
+  int n_obs_update;           // obstacles[0..n) get new pos/vel (setObstacles, cf_agent.cpp:63-70)
+  const double *new_pos, *new_vel;  // [n][3] live obstacle positions / velocities (device)
+  double *obs_pos, *obs_vel;  // [O][3] the agents' obstacle copy at rollout start (updated here)
+  const double *obs_rad;      // [O] radii from init()
+  const unsigned char *real_known;  // [O]
+  unsigned char *image;       // staging image to (re)build
+  float margin;               // broad-phase safety margin (absolute, metres)
+  int do_agents;              // 0: only rebuild the staging image
+  int set_known;              // 1: known := real agent's flags for the passed obstacles
+  int reset_velocity;         // 1: vel := clamp(v); min_obs_dist := shell
+};
+
+// grid: ceil(A / blockDim) blocks (1 block when !do_agents); block 0 also rebuilds the staging image.
+__global__ void __launch_bounds__(128) reset_kernel(const PlannerDev P, const ResetArgs R) {
+  __shared__ uint32_t s_bits[kMaxObstacles / 32], s_keep[kMaxObstacles / 32];
+  if (blockIdx.x == 0) {
+    double *px = reinterpret_cast<double *>(R.image + P.img.off_px);
+    double *py = reinterpret_cast<double *>(R.image + P.img.off_py);
+    double *pz = reinterpret_cast<double *>(R.image + P.img.off_pz);
+    double *rs = reinterpret_cast<double *>(R.image + P.img.off_rs);
+    float4 *bp = reinterpret_cast<float4 *>(R.image + P.img.off_bp);
+    for (int i = threadIdx.x; i < P.n_obs; i += blockDim.x) {
+      v3 op, ov;
+      if (i < R.n_obs_update) {
+        op = ld3(R.new_pos + 3 * i), ov = ld3(R.new_vel + 3 * i);
+        st3(R.obs_pos + 3 * i, op), st3(R.obs_vel + 3 * i, ov);
+      } else {
+        op = ld3(R.obs_pos + 3 * i), ov = ld3(R.obs_vel + 3 * i);
+      }
+      const double rsum = P.rad + R.obs_rad[i];
+      px[i] = op.x, py[i] = op.y, pz[i] = op.z, rs[i] = rsum;
+      if (P.img.dynamic) {
+        reinterpret_cast<double *>(R.image + P.img.off_vx)[i] = ov.x;
+        reinterpret_cast<double *>(R.image + P.img.off_vy)[i] = ov.y;
+        reinterpret_cast<double *>(R.image + P.img.off_vz)[i] = ov.z;
+        reinterpret_cast<double *>(R.image + P.img.off_dx)[i] = ov.x * P.pred_dt;  // getVelocity() * delta_t (:273)
+        reinterpret_cast<double *>(R.image + P.img.off_dy)[i] = ov.y * P.pred_dt;
+        reinterpret_cast<double *>(R.image + P.img.off_dz)[i] = ov.z * P.pred_dt;
+      }
+      bp[i] = broad_phase_record(op, P.shell, rsum, R.margin);
+    }
+  }
+  if (!R.do_agents) return;
+  if (R.set_known) {  // pack the real agent's flags once per block
+    for (int w = threadIdx.x; w < P.known_words; w += blockDim.x) {
+      uint32_t bits = 0, keep = 0;
+      for (int b = 0; b < 32; ++b) {
+        const int i = w * 32 + b;
+        if (i < R.n_obs_update) bits |= (uint32_t)(R.real_known[i] != 0) << b;
+        else keep |= 1u << b;  // setObstacles only touches the obstacles of the passed list
+      }
+      s_bits[w] = bits, s_keep[w] = keep;
+    }
+    __syncthreads();
+  }
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.n_agents) return;
+  v3 pos, vel;
+  if (R.from_real) {
+    pos = ld3(R.real->pos), vel = ld3(R.real->vel);
+  } else {
+    pos = ld3(R.pos_vel), vel = ld3(R.pos_vel + 3);
+  }
+  st3(P.cur_pos + 3 * a, pos);  // setPosition: path := [pos]
+  st3(P.paths + (size_t)a * P.max_steps * 3, pos);
+  P.n_path[a] = 1;
+  P.path_len[a] = 0.0;
+  P.ws_cost[a] = P.fused_valid ? add_workspace_cost(0.0, pos, P.fused_cost.ws, P.fused_cost.k_workspace) : 0.0;
+  if (R.reset_velocity) {
+    st3(P.vel + 3 * a, clamp_velocity(vel, P.vel_max));  // setVelocity
+    P.min_obs_dist[a] = P.shell;                         // resetMinObsDist
+  }
+  if (R.set_known) {
+    uint32_t *row = P.known + (size_t)a * P.known_words;
+    for (int w = 0; w < P.known_words; ++w) row[w] = (row[w] & s_keep[w]) | s_bits[w];
+  }
+}
+
+// ---- evaluateAgents (cf_manager.cpp:293-356) ---------------------------------------------------------------
+// workspace cost recomputed from the stored paths: used when the cost parameters differ from the
+// ones the rollout accumulated under (first tick, parameter change, setInitialPosition).
+__global__ void workspace_cost_kernel(const PlannerDev P, const CostParams C) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.n_agents) return;
+  const double *row = P.paths + (size_t)a * P.max_steps * 3;
+  double cost = 0.0;
+  const int n = P.n_path[a];
+  for (int k = 0; k < n; ++k) cost = add_workspace_cost(cost, ld3(row + 3 * k), C.ws, C.k_workspace);
+  P.ws_cost[a] = cost;
+}
+
+struct ArgminRecord {  // one rank's contribution to the global best-agent selection
+  double min_cost;     // DBL_MAX if no agent beat it (serial scan start value, :336)
+  double incumbent_cost;  // cost of the incumbent if this rank owns it, else NaN
+  int min_index;       // GLOBAL index of the local serial argmin, INT_MAX if none
+  int owns_incumbent;
+};
+
+// single block: per-agent costs, serial-order argmin (strict <, lowest index), then — unsharded —
+// hysteresis and incumbent update.
+__global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, const CostParams C, DeviceBest *best,
+                                                        double *best_random, ArgminRecord *rec, EvalResult *out,
+                                                        int finalize) {
+  __shared__ double s_cost[32];
+  __shared__ int s_idx[32];
+  const v3 goal = ld3(P.goal);
+  double bc = 1.7976931348623157e308;  // std::numeric_limits<double>::max()
+  int bi = 0x7fffffff;
+  for (int a = threadIdx.x; a < P.n_agents; a += blockDim.x) {
+    const double goal_dist = norm3(sub3(goal, ld3(P.cur_pos + 3 * a)));
+    const double c = finish_cost(P.ws_cost[a], goal_dist, P.approach_dist, C.k_goal_dist, P.path_len[a],
+                                 C.k_path_len, C.k_safe_dist, P.min_obs_dist[a]);
+    P.cost[a] = c;
+    if (c < bc) bc = c, bi = P.first_agent + a;  // ascending a: first index of the minimum
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (oc < bc || (oc == bc && oi < bi)) bc = oc, bi = oi;
+  }
+  if ((threadIdx.x & 31) == 0) s_cost[threadIdx.x >> 5] = bc, s_idx[threadIdx.x >> 5] = bi;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = (blockDim.x + 31) >> 5;
+    bc = threadIdx.x < nw ? s_cost[threadIdx.x] : 1.7976931348623157e308;
+    bi = threadIdx.x < nw ? s_idx[threadIdx.x] : 0x7fffffff;
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (oc < bc || (oc == bc && oi < bi)) bc = oc, bi = oi;
+    }
+    if (threadIdx.x == 0) {
+      s_cost[0] = bc, s_idx[0] = bi;
+    }
+  }
+  __syncthreads();
+  bc = s_cost[0], bi = s_idx[0];
+  const int inc_local = best->present ? best->id - 1 - P.first_agent : -1;
+  const bool owns = inc_local >= 0 && inc_local < P.n_agents;
+  if (threadIdx.x == 0) {
+    rec->min_cost = bc;
+    rec->min_index = bi;
+    rec->owns_incumbent = owns;
+    rec->incumbent_cost = owns ? P.cost[inc_local] : __longlong_as_double(0x7ff8000000000000LL);
+  }
+  if (!finalize) return;
+  // unsharded: min_cost_idx defaults to 0 when no cost is below DBL_MAX (:335-342)
+  const int min_idx = bi == 0x7fffffff ? 0 : bi;
+  const double min_cost = P.cost[min_idx - P.first_agent];
+  bool take = true;
+  int result = min_idx;
+  if (best->present && owns) {  // hysteresis :343-350 (the reference reads out of range if id-1 >= A)
+    if (!(min_cost < 0.9 * P.cost[inc_local])) take = false, result = best->id - 1;
+  }
+  __syncthreads();
+  if (take) {  // best_agent_ = ee_agents_[min]->makeCopy(): type, id and the RANDOM agent's vectors
+    const double *src = P.random_vecs + (size_t)(min_idx - P.first_agent) * P.n_obs * 3;
+    for (int i = threadIdx.x; i < P.n_obs * 3; i += blockDim.x) best_random[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    out->argmin_index = min_idx;
+    out->argmin_cost = min_cost;
+    out->incumbent_changed = take;
+    out->best_index = result;
+    out->best_cost = P.cost[result - P.first_agent];
+    if (take) {
+      best->present = 1;
+      best->id = min_idx + 1;
+      best->type = agent_type_of_index(min_idx);
+    }
+  }
+}
+
+// ---- moveRealEEAgent (cf_manager.cpp:257-263 -> RealCfAgent::cfPlanner, cf_agent.cpp:343-366) ------------------
+struct RealArgs {
+  RealState *real;
+  unsigned char *known;   // [O] real agent's known_obstacles_
+  double *rot;            // [O][3] real agent's field_rotation_vecs_
+  const DeviceBest *best;
+  const double *best_random;  // [O][3] incumbent's random vectors
+  const double *obs_pos, *obs_vel, *obs_rad;  // live list
+  int n_obs;
+  double delta_t;
+  int steps;
+  int agent_id;           // GLOBAL index whose gains are used; -1: eval->best_index (fused tick)
+  const EvalResult *eval;
+  double *path_out;       // [steps][3] position after every step (RealCfAgent::setPosition appends)
+  double goal[3];
+};
+
+// one warp
+__global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, const RealArgs R) {
+  const Group<32> g;
+  LiveObstacles obs;
+  obs.p = R.obs_pos, obs.v = R.obs_vel, obs.r = R.obs_rad, obs.agent_rad = P.rad;
+  KnownBytes known;
+  known.b = R.known;
+  int aid = R.agent_id;
+  if (aid < 0) aid = R.eval->best_index;
+  StepGains k;
+  k.k_attr = P.k_attr[aid], k.k_circ = P.k_circ[aid], k.k_repel = P.k_repel[aid], k.k_damp = P.k_damp[aid];
+  const int type = R.best->type;
+  const v3 goal = ld3(R.goal);
+  const v3 init_pos = ld3(R.real->init_pos);
+  v3 p = ld3(R.real->pos), v = ld3(R.real->vel);
+  v3 force = mk3(0.0, 0.0, 0.0);
+  const int n_field = R.n_obs - 1;
+  for (int s = 0; s < R.steps; ++s) {
+    force = mk3(0.0, 0.0, 0.0);
+    double k_goal_scale = 1.0;
+    const double dist_goal = norm3(sub3(goal, p));
+    if (field_gate_open(dist_goal, p, v, init_pos, P.approach_dist, P.vel_max)) {
+      double min_d, closest_d;
+      int closest_i;
+      field_pass(g, obs, n_field, nullptr, n_field, type, p, v, goal, P.shell, k.k_circ, known, R.rot,
+                     R.best_random, force, min_d, closest_d, closest_i);
+      if (norm3(force) > 1e-5) {
+        k_goal_scale = closest_i < 0 ? 1.0
+                                     : attractor_scaling(sub3(goal, p), p, v, P.vel_max, P.shell, closest_d,
+                                                         obs.pos(closest_i));
+      }
+      g.sync();
+    }
+    force = add_repel_force(force, p, obs.pos(R.n_obs - 1), obs.rsum(R.n_obs - 1), P.shell, k.k_repel);
+    force = add_attractor_force(force, sub3(goal, p), v, k.k_attr, k.k_damp, k_goal_scale, P.vel_max);
+    integrate_step(force, P.mass, R.delta_t, P.vel_max, p, v);
+    if (g.gl == 0) st3(R.path_out + 3 * s, p);
+  }
+  if (g.gl == 0 && R.steps > 0) {
+    st3(R.real->pos, p), st3(R.real->vel, v), st3(R.real->force, force);
+  }
+}
+
+// fill rot[A][O][3] with the default (0,0,1) (cf_agent.h:92-96) and clear known bits
+__global__ void init_state_kernel(const PlannerDev P, const double *init_pos) {
+  const size_t n = (size_t)P.n_agents * P.n_obs;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    P.rot[3 * i] = 0.0, P.rot[3 * i + 1] = 0.0, P.rot[3 * i + 2] = 1.0;
+  }
+  const size_t nk = (size_t)P.n_agents * P.known_words;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nk; i += (size_t)gridDim.x * blockDim.x)
+    P.known[i] = 0u;
+  for (size_t a = blockIdx.x * (size_t)blockDim.x + threadIdx.x; a < (size_t)P.n_agents;
+       a += (size_t)gridDim.x * blockDim.x) {
+    const v3 ip = ld3(init_pos);
+    // CfAgent constructor (cf_agent.h:69-91): path = [agent_pos], vel = (0.01,0,0), init_pos = 0
+    st3(P.cur_pos + 3 * a, ip);
+    st3(P.paths + a * P.max_steps * 3, ip);
+    st3(P.vel + 3 * a, mk3(0.01, 0.0, 0.0));
+    st3(P.init_pos + 3 * a, mk3(0.0, 0.0, 0.0));
+    P.min_obs_dist[a] = P.shell;
+    P.path_len[a] = 0.0;
+    P.ws_cost[a] = 0.0;
+    P.pred_time_ns[a] = 0.0;
+    P.n_path[a] = 1;
+    P.reached[a] = 0;
+    P.cost[a] = 0.0;
+  }
+}
+
+// setInitialPosition (cf_manager.cpp:226-236): agents' init_pos := pos, path := [pos]
+__global__ void set_initial_position_kernel(const PlannerDev P, const double *pos6) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.n_agents) return;
+  const v3 pos = ld3(pos6);
+  st3(P.init_pos + 3 * a, pos);
+  st3(P.cur_pos + 3 * a, pos);
+  st3(P.paths + (size_t)a * P.max_steps * 3, pos);
+  P.n_path[a] = 1;
+  P.path_len[a] = 0.0;
+  P.ws_cost[a] = 0.0;
+}
+
+}  // namespace pmaf

@@ -1,0 +1,354 @@
+"""Host-side mirror of the reference's planner API over libpmaf.so (include/pmaf.h).
+
+`CfManager` exposes the methods the planner node calls on
+ghostplanner::cfplanner::CfManager (/root/reference/src/bimanual_planning_ros/include/
+bimanual_planning_ros/cf_manager.h:36-136; call sites in src/panda_bimanual_control.cpp:329-369,
+:463-471, :494-521) with snake_case names, numpy arrays for Eigen vectors / Obstacle lists, and
+the reference's error behaviour mapped to exceptions (`PmafError`, carrying the C status).
+
+There is no CPU implementation behind this class: if libpmaf.so is missing, or no sm_100 GPU is
+visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmaf.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class PmafError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"pmaf status {status}: {message}")
+        self.status = status
+
+
+class Counters(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("rollouts", C.c_uint64), ("agent_steps", C.c_uint64), ("agent_steps_total", C.c_uint64),
+                ("last_rollout_ms", C.c_double), ("rollout_ms_total", C.c_double), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("lanes_per_agent", C.c_int), ("block_threads", C.c_int),
+                ("grid_blocks", C.c_int), ("smem_bytes", C.c_int)]
+
+
+# every symbol include/pmaf.h declares (tests check that the library exports all of them)
+API_SYMBOLS = [
+    "pmaf_last_error", "pmaf_version", "pmaf_create", "pmaf_destroy", "pmaf_set_shard", "pmaf_set_nccl_comm",
+    "pmaf_init", "pmaf_seed_random_vecs", "pmaf_set_random_vecs", "pmaf_get_random_vecs",
+    "pmaf_set_initial_position", "pmaf_set_real_position", "pmaf_start_prediction", "pmaf_stop_prediction",
+    "pmaf_evaluate_agents", "pmaf_move_real_agent", "pmaf_reset_agents", "pmaf_tick", "pmaf_get_num_agents",
+    "pmaf_get_next_position", "pmaf_get_next_velocity", "pmaf_get_ee_force", "pmaf_get_goal_position",
+    "pmaf_get_initial_position", "pmaf_get_dist_from_goal", "pmaf_get_best_agent_type", "pmaf_get_best_agent_id",
+    "pmaf_get_num_prediction_steps", "pmaf_get_real_num_prediction_steps", "pmaf_get_agent_summaries",
+    "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
+    "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters",
+    "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
+    "pmaf_flush_l2", "pmaf_measure_fp64_peak",
+]
+
+
+def build(verbose=False):
+    """Compile libpmaf.so in-tree for sm_100a (csrc/Makefile)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("building libpmaf.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libpmaf.so and declare its prototypes. Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.pmaf_last_error.restype = C.c_char_p
+    lib.pmaf_version.restype = C.c_char_p
+    lib.pmaf_create.argtypes = [C.POINTER(H), C.c_int]
+    lib.pmaf_destroy.argtypes = [H]
+    lib.pmaf_set_shard.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.pmaf_set_nccl_comm.argtypes = [H, C.c_void_p]
+    lib.pmaf_init.argtypes = [H, _dp, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
+                              _dp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_double]
+    lib.pmaf_seed_random_vecs.argtypes = [H, C.c_uint64]
+    lib.pmaf_set_random_vecs.argtypes = [H, _dp, C.c_int, C.c_int]
+    lib.pmaf_get_random_vecs.argtypes = [H, _dp, C.c_int, C.c_int]
+    lib.pmaf_set_initial_position.argtypes = [H, _dp]
+    lib.pmaf_set_real_position.argtypes = [H, _dp]
+    lib.pmaf_start_prediction.argtypes = [H]
+    lib.pmaf_stop_prediction.argtypes = [H]
+    lib.pmaf_evaluate_agents.argtypes = [H, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         _dp, _ip]
+    lib.pmaf_move_real_agent.argtypes = [H, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int]
+    lib.pmaf_reset_agents.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
+    lib.pmaf_tick.argtypes = [H, _dp, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                              C.c_double, _dp, _ip, _dp, _dp]
+    lib.pmaf_get_num_agents.argtypes = [H, _ip]
+    for n in ("pmaf_get_next_position", "pmaf_get_next_velocity", "pmaf_get_ee_force", "pmaf_get_goal_position",
+              "pmaf_get_initial_position", "pmaf_get_dist_from_goal"):
+        getattr(lib, n).argtypes = [H, _dp]
+    lib.pmaf_get_best_agent_type.argtypes = [H, _ip]
+    lib.pmaf_get_best_agent_id.argtypes = [H, _ip]
+    lib.pmaf_get_num_prediction_steps.argtypes = [H, C.c_int, _ip]
+    lib.pmaf_get_real_num_prediction_steps.argtypes = [H, _ip]
+    lib.pmaf_get_agent_summaries.argtypes = [H, _ip, _dp, _dp, _ip, _dp, _ip]
+    lib.pmaf_get_predicted_paths.argtypes = [H, _dp, C.c_int]
+    lib.pmaf_get_predicted_path.argtypes = [H, C.c_int, _dp, C.c_int, _ip]
+    lib.pmaf_get_agent_velocities.argtypes = [H, _dp]
+    lib.pmaf_get_planned_trajectory.argtypes = [H, _dp, C.c_int, _ip]
+    lib.pmaf_get_obstacle_state.argtypes = [H, C.c_int, _ip, _dp]
+    lib.pmaf_get_costs.argtypes = [H, _dp]
+    lib.pmaf_get_counters.argtypes = [H, C.POINTER(Counters)]
+    lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int]
+    lib.pmaf_set_upload_dedup.argtypes = [H, C.c_int]
+    lib.pmaf_timer_start.argtypes = [H]
+    lib.pmaf_timer_stop.argtypes = [H, _dp]
+    lib.pmaf_flush_l2.argtypes = [H]
+    lib.pmaf_measure_fp64_peak.argtypes = [H, _dp]
+    _lib = lib
+    return lib
+
+
+def _f64(x, shape=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    return a.reshape(shape) if shape is not None else a
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class CfManager:
+    """ghostplanner::cfplanner::CfManager over the C ABI. One instance = one planner on one GPU."""
+
+    def __init__(self, device=0, lanes_per_agent=0, block_threads=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self._check(self.lib.pmaf_create(C.byref(self.h), int(device)))
+        if lanes_per_agent or block_threads:
+            self._check(self.lib.pmaf_set_tuning(self.h, int(lanes_per_agent), int(block_threads)))
+        self.A = self.O = self.H = 0
+        self.n_global = 0
+        self.first_agent = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PmafError(rc, self.lib.pmaf_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pmaf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ----------------------------------------------------------------------
+    def set_shard(self, n_global, first_agent, rank, world):
+        self._check(self.lib.pmaf_set_shard(self.h, n_global, first_agent, rank, world))
+        self.first_agent = first_agent
+
+    def seed_random_vecs(self, seed):
+        self._check(self.lib.pmaf_seed_random_vecs(self.h, int(seed)))
+
+    def set_tuning(self, lanes_per_agent=0, block_threads=0):
+        self._check(self.lib.pmaf_set_tuning(self.h, int(lanes_per_agent), int(block_threads)))
+
+    def init(self, goal, delta_t, obs_pos, obs_vel, obs_rad, k_attr, k_circ, k_repel, k_damp, k_manip,
+             k_repel_force=(), velocity_max=0.5, approach_dist=0.25, detect_shell_rad=0.8,
+             max_prediction_steps=1500, prediction_freq_multiple=1, agent_mass=1.0, radius=0.05):
+        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        ka, kc, kr, kd, km = (_f64(x, (-1,)) for x in (k_attr, k_circ, k_repel, k_damp, k_manip))
+        kf = _f64(k_repel_force, (-1,))
+        if not (len(ka) == len(kc) == len(kr) == len(km)):  # the reference asserts this (cf_manager.cpp:50-51)
+            raise PmafError(-1, "gain vectors differ in length")
+        self._check(self.lib.pmaf_init(self.h, _d(_f64(goal, (3,))), float(delta_t), len(orad), _d(op), _d(ov),
+                                       _d(orad), len(ka), _d(ka), _d(kc), _d(kr), _d(kd), _d(km), len(kf), _d(kf),
+                                       float(velocity_max), float(approach_dist), float(detect_shell_rad),
+                                       int(max_prediction_steps), int(prediction_freq_multiple), float(agent_mass),
+                                       float(radius)))
+        n = C.c_int()
+        self._check(self.lib.pmaf_get_num_agents(self.h, C.byref(n)))
+        self.A, self.O, self.H, self.n_global = n.value, len(orad), int(max_prediction_steps), max(len(ka), 1)
+
+    def set_random_vecs(self, vecs):
+        v = _f64(vecs)
+        self._check(self.lib.pmaf_set_random_vecs(self.h, _d(v), v.shape[0], v.shape[1]))
+
+    def get_random_vecs(self):
+        v = np.zeros((self.A, self.O, 3))
+        self._check(self.lib.pmaf_get_random_vecs(self.h, _d(v), self.A, self.O))
+        return v
+
+    # ---- the per-tick calls (planCallback order) ---------------------------------------------------
+    def set_initial_position(self, p):
+        self._check(self.lib.pmaf_set_initial_position(self.h, _d(_f64(p, (3,)))))
+
+    def set_real_position(self, p):
+        self._check(self.lib.pmaf_set_real_position(self.h, _d(_f64(p, (3,)))))
+
+    def start_prediction(self):
+        self._check(self.lib.pmaf_start_prediction(self.h))
+
+    def stop_prediction(self):
+        self._check(self.lib.pmaf_stop_prediction(self.h))
+
+    def evaluate_agents(self, obs_pos, obs_vel, obs_rad, k_goal_dist, k_path_len, k_safe_dist, k_workspace,
+                        ws_limits):
+        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        best = C.c_int()
+        self._check(self.lib.pmaf_evaluate_agents(self.h, len(orad), _d(op), _d(ov), _d(orad), float(k_goal_dist),
+                                                  float(k_path_len), float(k_safe_dist), float(k_workspace),
+                                                  _d(_f64(ws_limits, (6,))), C.byref(best)))
+        return best.value
+
+    def move_real_agent(self, obs_pos, obs_vel, obs_rad, delta_t, steps, agent_id):
+        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        self._check(self.lib.pmaf_move_real_agent(self.h, len(orad), _d(op), _d(ov), _d(orad), float(delta_t),
+                                                  int(steps), int(agent_id)))
+
+    def reset_agents(self, pos, vel, obs_pos, obs_vel, obs_rad):
+        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        self._check(self.lib.pmaf_reset_agents(self.h, _d(_f64(pos, (3,))), _d(_f64(vel, (3,))), len(orad), _d(op),
+                                               _d(ov), _d(orad)))
+
+    def tick(self, obs_pos, obs_vel, obs_rad, delta_t, k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits,
+             measured_position=None):
+        """One whole planCallback as a device-resident chain (pmaf_tick)."""
+        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        best = C.c_int()
+        p, v = np.zeros(3), np.zeros(3)
+        meas = _d(_f64(measured_position, (3,))) if measured_position is not None else None
+        self._check(self.lib.pmaf_tick(self.h, meas, len(orad), _d(op), _d(ov), _d(orad), float(delta_t),
+                                       float(k_goal_dist), float(k_path_len), float(k_safe_dist), float(k_workspace),
+                                       _d(_f64(ws_limits, (6,))), C.byref(best), _d(p), _d(v)))
+        return best.value, p, v
+
+    # ---- getters ----------------------------------------------------------------------------------
+    def _vec3(self, fn):
+        v = np.zeros(3)
+        self._check(fn(self.h, _d(v)))
+        return v
+
+    def get_next_position(self):
+        return self._vec3(self.lib.pmaf_get_next_position)
+
+    def get_next_velocity(self):
+        return self._vec3(self.lib.pmaf_get_next_velocity)
+
+    def get_ee_force(self):
+        return self._vec3(self.lib.pmaf_get_ee_force)
+
+    def get_goal_position(self):
+        return self._vec3(self.lib.pmaf_get_goal_position)
+
+    def get_initial_position(self):
+        return self._vec3(self.lib.pmaf_get_initial_position)
+
+    def get_dist_from_goal(self):
+        d = C.c_double()
+        self._check(self.lib.pmaf_get_dist_from_goal(self.h, C.byref(d)))
+        return d.value
+
+    def get_best_agent_type(self):
+        t = C.c_int()
+        self._check(self.lib.pmaf_get_best_agent_type(self.h, C.byref(t)))
+        return t.value
+
+    def get_best_agent_id(self):
+        t = C.c_int()
+        self._check(self.lib.pmaf_get_best_agent_id(self.h, C.byref(t)))
+        return t.value
+
+    def get_num_prediction_steps(self, agent):
+        t = C.c_int()
+        self._check(self.lib.pmaf_get_num_prediction_steps(self.h, int(agent), C.byref(t)))
+        return t.value
+
+    def get_agent_summaries(self):
+        A = self.A
+        steps, reached, types = (np.zeros(A, dtype=np.int32) for _ in range(3))
+        length, mind, t = (np.zeros(A) for _ in range(3))
+        self._check(self.lib.pmaf_get_agent_summaries(self.h, _i(steps), _d(length), _d(mind), _i(reached), _d(t),
+                                                      _i(types)))
+        return dict(steps=steps, length=length, min_obs_dist=mind, reached=reached, pred_time_ns=t, agent_type=types)
+
+    def get_predicted_paths(self, stride=None):
+        stride = int(stride or self.H)
+        out = np.full((self.A, stride, 3), np.nan)
+        self._check(self.lib.pmaf_get_predicted_paths(self.h, _d(out), stride))
+        return out
+
+    def get_predicted_path(self, agent):
+        out = np.zeros((self.H, 3))
+        n = C.c_int()
+        self._check(self.lib.pmaf_get_predicted_path(self.h, int(agent), _d(out), self.H, C.byref(n)))
+        return out[: n.value]
+
+    def get_agent_velocities(self):
+        out = np.zeros((self.A, 3))
+        self._check(self.lib.pmaf_get_agent_velocities(self.h, _d(out)))
+        return out
+
+    def get_planned_trajectory(self):
+        n = C.c_int()
+        self._check(self.lib.pmaf_get_planned_trajectory(self.h, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 3))
+        self._check(self.lib.pmaf_get_planned_trajectory(self.h, _d(out), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def get_obstacle_state(self):
+        known = np.zeros((self.A + 1, self.O), dtype=np.int32)
+        rot = np.zeros((self.A + 1, self.O, 3))
+        self._check(self.lib.pmaf_get_obstacle_state(self.h, self.O, _i(known), _d(rot)))
+        return known, rot
+
+    def get_costs(self):
+        c = np.zeros(self.A)
+        self._check(self.lib.pmaf_get_costs(self.h, _d(c)))
+        return c
+
+    def counters(self):
+        c = Counters()
+        self._check(self.lib.pmaf_get_counters(self.h, C.byref(c)))
+        return {f[0]: getattr(c, f[0]) for f in Counters._fields_}
+
+    def set_upload_dedup(self, dedup):
+        self._check(self.lib.pmaf_set_upload_dedup(self.h, 1 if dedup else 0))
+
+    def timer_start(self):
+        self._check(self.lib.pmaf_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.pmaf_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._check(self.lib.pmaf_flush_l2(self.h))
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        self._check(self.lib.pmaf_measure_fp64_peak(self.h, C.byref(t)))
+        return t.value

@@ -1,0 +1,194 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI of
+libpmaf.so via pmaf_b200.planner.CfManager and is compared with
+
+  * the golden vectors frozen from the REFERENCE build (tests/golden/*.npz) on every named case,
+  * the C oracle on the same seeded inputs at the BASELINE.json sizes the oracle finishes in
+    seconds, and
+  * size-independent properties (serial-order argmin, lane-count invariance, fused == call-by-call,
+    executed-step count) at full size.
+
+Bars: bit-exact for indices, counts and flags; paths, velocities, lengths and distances within
+the north-star tolerance RTOL = 1e-5 relative (|err| <= RTOL * max(|ref|, 1)). The kernels
+reproduce the reference's operation order, so the observed error is far smaller: the only
+arithmetic that is not bit-identical by construction is exp() in attractorForceScaling (CUDA
+libdevice vs glibc, both < 1 ulp); the fraction of bit-identical values is written to
+gpurun_out/parity_report.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from pmaf_b200 import cases, loop, scenarios
+from parity import FLOAT_KEYS, INDEX_KEYS, assert_bit_identical, assert_close
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative fp tolerance"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = cases.all_cases()
+REPORT = {}
+
+
+def _planner(**kw):
+    from pmaf_b200.planner import CfManager
+
+    return CfManager(0, **kw)
+
+
+def _bit_stats(got, want):
+    tot = same = 0
+    worst = 0.0
+    for k in FLOAT_KEYS:
+        if k in got and k in want:
+            a, b = np.asarray(got[k], dtype=np.float64), np.asarray(want[k], dtype=np.float64)
+            eq = (a == b) | (np.isnan(a) & np.isnan(b))
+            tot += eq.size
+            same += int(eq.sum())
+            with np.errstate(invalid="ignore"):
+                err = np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+            if np.any(~eq):
+                worst = max(worst, float(np.nanmax(np.where(eq, 0.0, err))))
+    return dict(values=tot, bit_identical=same, worst_rel_err=worst)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _write_report():
+    yield
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_case_matches_reference_golden(name):
+    want = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    p = _planner()
+    got = CASES[name](p)
+    p.close()
+    REPORT[name] = _bit_stats(got, want)
+    assert_bit_identical(got, want, keys=INDEX_KEYS, ctx=f"{name}: ")
+    assert_close(got, want, RTOL, ctx=f"{name}: ")
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16])
+@pytest.mark.parametrize("name", ["near326_switching", "moving1", "rand5_many_agents", "rand6_many_obstacles"])
+def test_lane_count_does_not_change_results(name, lanes):
+    """Sub-warp groups reorder nothing: forces are summed in obstacle order whatever the lane count."""
+    a = CASES[name](_planner())
+    b = CASES[name](_planner(lanes_per_agent=lanes))
+    assert_bit_identical(b, a, ctx=f"{name} lanes={lanes}: ")
+
+
+@pytest.mark.parametrize("name", ["anchor_A8_H50", "near326_switching", "moving0", "had_nan_on_axis"])
+def test_fused_tick_equals_call_by_call(name):
+    """pmaf_tick (device-resident chain) == the five CfManager calls of planCallback."""
+    sc = CASES[name].scenario
+    ticks = 40
+    a = loop.run_closed_loop(_planner(), sc, ticks, record_paths=True)
+    p = _planner()
+    feed = loop.ObstacleFeed(sc)
+    loop.plan_begin(p, sc)
+    best, pos, vel, paths, steps = [], [], [], [], []
+    for _ in range(ticks):
+        b, x, v = p.tick(feed.pos, feed.vel, feed.rad, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                         sc.k_workspace, sc.ws_limits)
+        best.append(b), pos.append(x), vel.append(v)
+        p.stop_prediction()
+        paths.append(p.get_predicted_paths())
+        steps.append(p.get_agent_summaries()["steps"].copy())
+        feed.step()
+    got = dict(best=np.array(best), next_pos=np.array(pos), next_vel=np.array(vel), paths=np.array(paths),
+               steps=np.array(steps))
+    assert_bit_identical(got, a, keys=list(got), ctx=f"{name}: ")
+
+
+def _oracle():
+    from oracle import cpu_planners
+
+    if not cpu_planners.have_oracle():
+        cpu_planners.build("oracle")
+    return cpu_planners.OraclePlanner()
+
+
+@pytest.mark.parametrize("make,ticks", [(scenarios.c2, 6), (scenarios.c5, 4)])
+def test_baseline_config_against_oracle(make, ticks):
+    sc = make()
+    want = loop.run_closed_loop(_oracle(), sc, ticks, record_paths=True)
+    got = loop.run_closed_loop(_planner(), sc, ticks, record_paths=True)
+    REPORT[sc.name] = _bit_stats(dict(got, final_paths=got["paths"]), dict(want, final_paths=want["paths"]))
+    assert_bit_identical(got, want, keys=("best", "steps", "reached"), ctx=f"{sc.name}: ")
+    assert_close(got, want, RTOL, keys=("next_pos", "next_vel", "length", "min_obs_dist", "goal_dist", "paths"),
+                 ctx=f"{sc.name}: ")
+    # every integration step executes on these workloads
+    assert int(got["steps"][-1].sum()) == sc.num_agents * sc.max_prediction_steps
+
+
+def test_c3_full_size_properties():
+    """4096 agents x 256 obstacles x 500: properties that do not need the oracle."""
+    sc = scenarios.c3()
+    p = _planner()
+    feed = loop.ObstacleFeed(sc)
+    loop.plan_begin(p, sc)
+    for t in range(3):
+        best, _, _ = loop.control_tick(p, sc, feed)
+        p.stop_prediction()
+        if t == 0:
+            assert best == 0  # quirk 7: equal costs on the first tick
+    s = p.get_agent_summaries()
+    assert int(s["steps"].sum()) == sc.num_agents * sc.max_prediction_steps
+    assert np.all(np.isfinite(s["length"])) and np.all(s["min_obs_dist"] >= 1e-5)
+    c = p.counters()
+    assert c["agent_steps"] == sc.num_agents * (sc.max_prediction_steps - 1)
+    # best-agent selection is bit-identical to a serial argmin + hysteresis over the device costs
+    inc = p.get_best_agent_id() - 1
+    best = p.evaluate_agents(feed.pos, feed.vel, feed.rad, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                             sc.k_workspace, sc.ws_limits)
+    costs = p.get_costs()
+    m, mc = 0, np.finfo(np.float64).max
+    for i, cst in enumerate(costs):
+        if cst < mc:
+            m, mc = i, cst
+    want = m if costs[m] < 0.9 * costs[inc] else inc
+    assert best == want
+    # fused cost accumulation == recomputation from the stored paths (different cost parameters
+    # force the recompute kernel; then the original ones again)
+    p.evaluate_agents(feed.pos, feed.vel, feed.rad, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                      2.0 * sc.k_workspace, sc.ws_limits)
+    p.evaluate_agents(feed.pos, feed.vel, feed.rad, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                      sc.k_workspace, sc.ws_limits)
+    assert np.array_equal(p.get_costs(), costs)
+    # a sample of agents against the oracle's rollout from the same state is covered at C2 size;
+    # here: lane-count invariance at full size
+    paths32 = p.get_predicted_paths()
+    q = _planner(lanes_per_agent=8)
+    feed2 = loop.ObstacleFeed(sc)
+    loop.plan_begin(q, sc)
+    for t in range(3):
+        loop.control_tick(q, sc, feed2)
+    q.stop_prediction()
+    assert np.array_equal(q.get_predicted_paths(), paths32, equal_nan=True)
+
+
+def test_error_behaviour_matches_the_reference_contract():
+    from pmaf_b200.planner import PmafError
+
+    sc = scenarios.small_random(0)
+    p = _planner()
+    with pytest.raises(PmafError):  # nothing initialised yet
+        p.start_prediction()
+    loop.plan_begin(p, sc)
+    with pytest.raises(PmafError):  # no best agent before the first evaluate (null best_agent_ in the reference)
+        p.move_real_agent(sc.obs_pos, sc.obs_vel, sc.obs_rad, sc.delta_t, 1, 0)
+    with pytest.raises(PmafError):  # more obstacles than init() saw: std::out_of_range in the reference
+        big = np.zeros((sc.num_obstacles + 1, 3))
+        p.reset_agents(sc.start, np.zeros(3), big, big, np.ones(sc.num_obstacles + 1))
+    # start without reset after a finished rollout is a no-op
+    loop.control_tick(p, sc, loop.ObstacleFeed(sc))
+    p.stop_prediction()
+    before = p.get_predicted_paths()
+    p.start_prediction()
+    p.stop_prediction()
+    assert np.array_equal(before, p.get_predicted_paths(), equal_nan=True)
