@@ -79,8 +79,14 @@ int pmaf_destroy(pmaf_planner *p);
  * (cpp:70-104). With n_global == n_local (default) the planner is unsharded. */
 int pmaf_set_shard(pmaf_planner *p, int n_global, int first_agent, int rank, int world);
 
-/* Optional: attach an NCCL communicator (ncclComm_t passed as void*) used for the single
- * per-tick best-agent collective of a sharded planner. */
+/* Sharded planners exchange ONE NCCL all-gather per evaluate (per control tick): every rank's
+ * (min cost, argmin index, incumbent cost) record plus the random vectors of its local winner,
+ * 40 + 24*n_obs bytes per rank, followed by a replicated serial selection — bit-identical to the
+ * reference's serial argmin over the whole population. The communicator is either created here
+ * from an id made on one rank and distributed by the host (torch.distributed, MPI, ...), or
+ * attached from outside (ncclComm_t as void*). libnccl.so.2 is dlopen()ed on first use. */
+int pmaf_nccl_unique_id(unsigned char id_out[128]);
+int pmaf_nccl_init(pmaf_planner *p, const unsigned char id[128], int rank, int world);
 int pmaf_set_nccl_comm(pmaf_planner *p, void *nccl_comm);
 
 /* CfManager::init (h:93-102, cpp:41-124). n_agents = k_attr.size() (at least one agent — HAD —
@@ -186,6 +192,7 @@ int pmaf_get_costs(pmaf_planner *p, double *costs /* [n_agents] */);
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 typedef struct {
   uint64_t kernel_launches;  /* kernels of this library launched on the handle since create */
+  uint64_t collectives;      /* NCCL collectives enqueued since create */
   uint64_t rollouts;         /* rollout kernels among them */
   uint64_t agent_steps;      /* integration steps executed by the last completed rollout */
   uint64_t agent_steps_total; /* ... by all completed rollouts since create */

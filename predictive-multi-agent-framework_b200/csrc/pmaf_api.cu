@@ -2,6 +2,8 @@
 // buffers, one stream per planner, launches, tiny H2D/D2H copies. There is no CPU compute path:
 // every entry point that computes launches a kernel and fails with PMAF_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: libnccl is dlopen()ed when a planner is sharded
 
 #include <algorithm>
 #include <cmath>
@@ -102,7 +104,9 @@ struct pmaf_planner {
   DevBuf<RealState> real;
   DevBuf<DeviceBest> best;
   DevBuf<EvalResult> eval;
-  DevBuf<ArgminRecord> rec;
+  DevBuf<unsigned char> rec;       // this rank's ArgminRecord + random-vector row
+  DevBuf<unsigned char> rec_all;   // all-gathered records [world]
+  bool nccl_owned = false;
   DevBuf<unsigned long long> step_counter;
   DevBuf<unsigned char> l2_scratch;
   // host mirrors
@@ -136,6 +140,8 @@ struct pmaf_planner {
   int tune_lpa = 0, tune_block = 0;
   pmaf_counters ctr{};
 };
+
+static void nccl_release(pmaf_planner *p);
 
 static int set_device(pmaf_planner *p) {
   CU(cudaSetDevice(p->device));
@@ -257,6 +263,70 @@ static int finish_rollout(pmaf_planner *p) {
   return harvest_timing(p, p->roll_slot, true);
 }
 
+// ---- NCCL (dlopen) ----------------------------------------------------------------------------------------------
+struct NcclApi {
+  void *handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.handle) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  REQUIRE(g_nccl.handle != nullptr, PMAF_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.handle, "ncclAllGather");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
+  REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather, PMAF_ERR_NCCL,
+          "libnccl lacks a required symbol");
+  return 0;
+}
+
+#define NC(call)                                                                                       \
+  do {                                                                                                 \
+    ncclResult_t r_ = (call);                                                                          \
+    if (r_ != ncclSuccess)                                                                             \
+      return fail(PMAF_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+  } while (0)
+
+static void nccl_release(pmaf_planner *p) {
+  if (p->nccl && p->nccl_owned && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)p->nccl);
+  p->nccl = nullptr, p->nccl_owned = false;
+}
+
+extern "C" int pmaf_nccl_unique_id(unsigned char out[128]) {
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  if (int rc = nccl_load()) return rc;
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out, &id, 128);
+  return 0;
+}
+
+extern "C" int pmaf_nccl_init(pmaf_planner *p, const unsigned char id_bytes[128], int rank, int world) {
+  ENTER(p);
+  REQUIRE(id_bytes && world >= 1 && rank >= 0 && rank < world, PMAF_ERR_ARG, "pmaf_nccl_init: bad argument");
+  if (int rc = nccl_load()) return rc;
+  nccl_release(p);
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, 128);
+  ncclComm_t comm = nullptr;
+  NC(g_nccl.CommInitRank(&comm, world, id, rank));
+  p->nccl = comm, p->nccl_owned = true;
+  return 0;
+}
+
 // ---- lifecycle -------------------------------------------------------------------------------------------------
 extern "C" int pmaf_create(pmaf_planner **out, int device) {
   REQUIRE(out != nullptr, PMAF_ERR_ARG, "pmaf_create: out is null");
@@ -285,7 +355,7 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   memset(p->h_out, 0, sizeof(HostOut));
   CU(p->best.resize(1));
   CU(p->eval.resize(1));
-  CU(p->rec.resize(1));
+  CU(p->rec.resize(argmin_record_bytes(0)));
   CU(p->real.resize(1));
   CU(p->step_counter.resize(2));
   CU(p->scratch.resize(16));
@@ -310,6 +380,8 @@ extern "C" int pmaf_destroy(pmaf_planner *p) {
   p->l2_scratch.release();
   p->n_path.release(), p->reached.release(), p->known.release(), p->image.release(), p->real_known.release();
   p->real.release(), p->best.release(), p->eval.release(), p->rec.release(), p->step_counter.release();
+  p->rec_all.release();
+  nccl_release(p);
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_out) cudaFreeHost(p->h_out);
   for (cudaEvent_t e : {p->ev_roll[0][0], p->ev_roll[0][1], p->ev_roll[1][0], p->ev_roll[1][1], p->ev_d2h, p->ev_stage, p->ev_t0, p->ev_t1})
@@ -331,7 +403,9 @@ extern "C" int pmaf_set_shard(pmaf_planner *p, int n_global, int first_agent, in
 
 extern "C" int pmaf_set_nccl_comm(pmaf_planner *p, void *nccl_comm) {
   ENTER(p);
-  p->nccl = nccl_comm;
+  if (int rc = nccl_load()) return rc;
+  nccl_release(p);
+  p->nccl = nccl_comm, p->nccl_owned = false;
   return 0;
 }
 
@@ -438,6 +512,8 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
   CU(p->real_known.resize(O));
   CU(p->real_rot.resize(O * 3));
   CU(p->real_path_out.resize(256 * 3));
+  CU(p->rec.resize(argmin_record_bytes((int)O)));
+  CU(p->rec_all.resize(argmin_record_bytes((int)O) * (size_t)p->world));
   {  // best_agent_ survives init (quirk 6); keep the overlapping part of its random vectors
     DevBuf<double> old = p->best_random;
     const int old_n = p->best_n_obs;
@@ -676,8 +752,19 @@ static int launch_evaluate(pmaf_planner *p, const CostParams &C) {
   }
   p->last_cost = C, p->have_cost = true;
   const int threads = p->A >= 1024 ? 1024 : std::max(32, ((p->A + 31) / 32) * 32);
-  return launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, p->rec.p,
-                p->eval.p, 1);
+  ArgminRecord *rec = reinterpret_cast<ArgminRecord *>(p->rec.p);
+  if (p->world == 1)
+    return launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec, p->eval.p, 1);
+  // sharded: local scan -> ONE all-gather of (record + candidate random vectors) -> replicated selection
+  REQUIRE(p->nccl != nullptr, PMAF_ERR_STATE, "sharded planner without an NCCL communicator (pmaf_nccl_init)");
+  if (int rc = launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec,
+                      p->eval.p, 0))
+    return rc;
+  const size_t bytes = argmin_record_bytes(p->O);
+  NC(g_nccl.AllGather(p->rec.p, p->rec_all.p, bytes, ncclChar, (ncclComm_t)p->nccl, p->stream));
+  p->ctr.collectives++;
+  return launch(p, global_select_kernel, dim3(1), dim3(256), 0, (const unsigned char *)p->rec_all.p, p->world, p->O,
+                p->best.p, p->best_random.p, p->eval.p);
 }
 
 static CostParams make_cost(double k_goal_dist, double k_path_len, double k_safe_dist, double k_workspace,
@@ -696,7 +783,6 @@ extern "C" int pmaf_evaluate_agents(pmaf_planner *p, int n_obs, const double *ob
   NEED_INIT(p);
   (void)n_obs, (void)obs_pos, (void)obs_vel, (void)obs_rad;  // unused by the reference as well
   REQUIRE(ws_limits && best_index, PMAF_ERR_ARG, "pmaf_evaluate_agents: null argument");
-  REQUIRE(p->world == 1, PMAF_ERR_STATE, "pmaf_evaluate_agents: sharded planners evaluate through pmaf_tick");
   if (int rc = finish_rollout(p)) return rc;
   const CostParams C = make_cost(k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits);
   if (int rc = launch_evaluate(p, C)) return rc;
@@ -810,7 +896,6 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   NEED_INIT(p);
   REQUIRE(obs_pos && obs_vel && obs_rad && ws_limits, PMAF_ERR_ARG, "pmaf_tick: null argument");
   REQUIRE(n_obs >= 1 && n_obs <= p->O, PMAF_ERR_ARG, "pmaf_tick: n_obs=%d (planner has %d obstacles)", n_obs, p->O);
-  REQUIRE(p->world == 1, PMAF_ERR_STATE, "pmaf_tick: sharded planners need an NCCL communicator");
   if (measured_pos) {
     if (int rc = pmaf_set_real_position(p, measured_pos)) return rc;
   }

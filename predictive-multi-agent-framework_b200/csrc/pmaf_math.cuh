@@ -11,6 +11,10 @@
 // Division and sqrt are IEEE correctly rounded on both sides (nvcc default -prec-div/-prec-sqrt).
 #pragma once
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "pmaf_exp_table.inc"
 
 #if defined(__CUDACC__)
 #define PMAF_HD __host__ __device__ __forceinline__
@@ -72,6 +76,67 @@ PMAF_HD v3 normalized3(v3 a) {
 }
 // std::max(d, 1e-5) (cf_agent.cpp:85): NaN stays NaN
 PMAF_HD double clamp_dist(double d) { return d < 1e-5 ? 1e-5 : d; }
+
+// ---- exp() of the host libm ------------------------------------------------------------------------
+// attractorForceScaling calls std::exp (:220). CUDA's exp() and glibc's differ in the last bit for a
+// few percent of the arguments, and the rollout amplifies a one-ulp difference through its hard
+// thresholds, so the kernels evaluate exp with glibc's own algorithm (sysdeps/ieee754/dbl-64/e_exp.c,
+// ARM optimized-routines: N = 128 table + degree-5 polynomial) in the operation order of the FMA
+// build that x86-64 glibc selects at run time (__exp_fma): every a*b+c of the C source is one fused
+// multiply-add. tests/test_exp.py checks it bit for bit against the host's exp(). Constants and table
+// come from the system libm (tools/gen_exp_table.py).
+#if defined(__CUDACC__)
+static __device__ const uint64_t d_exp_tab[256] = {PMAF_EXP_TABLE};
+#endif
+static const uint64_t h_exp_tab[256] = {PMAF_EXP_TABLE};
+
+PMAF_HD uint64_t exp_tab(unsigned i) {
+#if defined(__CUDA_ARCH__)
+  return d_exp_tab[i];
+#else
+  return h_exp_tab[i];
+#endif
+}
+PMAF_HD uint64_t bits_of(double x) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t u;
+  memcpy(&u, &x, sizeof u);
+  return u;
+#endif
+}
+PMAF_HD double double_of(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double x;
+  memcpy(&x, &u, sizeof x);
+  return x;
+#endif
+}
+
+PMAF_HD double exp_glibc(double x) {
+  const unsigned abstop = (unsigned)(bits_of(x) >> 52) & 0x7ffu;
+  // main path of __exp: 2^-54 <= |x| < 512 (no special-casing of the scale needed)
+  if (abstop - 0x3c9u >= 0x408u - 0x3c9u) {
+    if (abstop < 0x3c9u) return 1.0 + x;  // tiny |x| (WANT_ROUNDING)
+    return exp(x);                         // |x| >= 512, inf, nan: outside the planner's domain
+  }
+  double kd = fma(kExpInvLn2N, x, kExpShift);
+  const uint64_t ki = bits_of(kd);
+  kd -= kExpShift;
+  const double r = fma(kd, kExpNegLn2loN, fma(kd, kExpNegLn2hiN, x));
+  const unsigned idx = 2u * (unsigned)(ki % 128u);
+  const uint64_t top = ki << (52 - 7);
+  const double tail = double_of(exp_tab(idx));
+  const uint64_t sbits = exp_tab(idx + 1) + top;
+  const double r2 = r * r;
+  const double p23 = fma(r, kExpC3, kExpC2), p45 = fma(r, kExpC5, kExpC4);
+  const double tmp = fma(r2 * r2, p45, fma(r2, p23, tail + r));
+  const double scale = double_of(sbits);
+  return fma(scale, tmp, scale);
+}
 
 // ---- rotation vectors (calculateRotationVector) ------------------------------------------------
 // to_obs = normalized(o_i - p), the same value circForce already formed for its skip test.
@@ -167,7 +232,7 @@ PMAF_HD v3 add_attractor_force(v3 force, v3 goal_vec, v3 v, double k_attr, doubl
 // closest_d, position o_c) is known
 PMAF_HD double attractor_scaling(v3 goal_vec, v3 p, v3 v, double vel_max, double shell, double closest_d, v3 o_c) {
   if (dot3(goal_vec, v) <= 0.0 && norm3(v) < vel_max - 0.1 * vel_max && norm3(goal_vec) > 0.15) return 0.0;
-  double w1 = 1 - exp(-sqrt(closest_d) / shell);
+  double w1 = 1 - exp_glibc(-sqrt(closest_d) / shell);
   v3 rov = sub3(o_c, p);
   double w2 = 1 - (dot3(goal_vec, rov) / (norm3(goal_vec) * norm3(rov)));
   w2 = w2 * w2;

@@ -306,9 +306,14 @@ __global__ void workspace_cost_kernel(const PlannerDev P, const CostParams C) {
 struct ArgminRecord {  // one rank's contribution to the global best-agent selection
   double min_cost;     // DBL_MAX if no agent beat it (serial scan start value, :336)
   double incumbent_cost;  // cost of the incumbent if this rank owns it, else NaN
+  double cost_agent0;  // cost of global agent 0 if owned (the scan's default result), else NaN
   int min_index;       // GLOBAL index of the local serial argmin, INT_MAX if none
   int owns_incumbent;
+  // followed in the exchange buffer by the local argmin agent's random vectors, double[O][3]
 };
+__host__ __device__ inline size_t argmin_record_bytes(int n_obs) {
+  return sizeof(ArgminRecord) + (size_t)n_obs * 3 * sizeof(double);
+}
 
 // single block: per-agent costs, serial-order argmin (strict <, lowest index), then — unsharded —
 // hysteresis and incumbent update.
@@ -352,12 +357,19 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, cons
   const int inc_local = best->present ? best->id - 1 - P.first_agent : -1;
   const bool owns = inc_local >= 0 && inc_local < P.n_agents;
   if (threadIdx.x == 0) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     rec->min_cost = bc;
     rec->min_index = bi;
     rec->owns_incumbent = owns;
-    rec->incumbent_cost = owns ? P.cost[inc_local] : __longlong_as_double(0x7ff8000000000000LL);
+    rec->incumbent_cost = owns ? P.cost[inc_local] : qnan;
+    rec->cost_agent0 = P.first_agent == 0 ? P.cost[0] : qnan;
   }
-  if (!finalize) return;
+  if (!finalize) {  // sharded: ship the local winner's random vectors with the record
+    double *row = reinterpret_cast<double *>(rec + 1);
+    const double *src = bi == 0x7fffffff ? nullptr : P.random_vecs + (size_t)(bi - P.first_agent) * P.n_obs * 3;
+    for (int i = threadIdx.x; i < P.n_obs * 3; i += blockDim.x) row[i] = src ? src[i] : 0.0;
+    return;
+  }
   // unsharded: min_cost_idx defaults to 0 when no cost is below DBL_MAX (:335-342)
   const int min_idx = bi == 0x7fffffff ? 0 : bi;
   const double min_cost = P.cost[min_idx - P.first_agent];
@@ -382,6 +394,43 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, cons
       best->id = min_idx + 1;
       best->type = agent_type_of_index(min_idx);
     }
+  }
+}
+
+// Sharded planners: after ONE all-gather of the per-rank records every rank repeats the reference's
+// serial scan over the ranks in order (ranks own contiguous ascending agent blocks, so "lowest index
+// wins" is preserved), applies the hysteresis and updates its replica of the incumbent.
+__global__ void __launch_bounds__(256) global_select_kernel(const unsigned char *records, int world, int n_obs,
+                                                            DeviceBest *best, double *best_random,
+                                                            EvalResult *out) {
+  __shared__ int s_take, s_min_rank;
+  const size_t stride = argmin_record_bytes(n_obs);
+  if (threadIdx.x == 0) {
+    double min_cost = 1.7976931348623157e308;
+    int min_idx = 0, min_rank = -1;
+    double inc_cost = 0.0, cost0 = 0.0;
+    bool have_inc = false;
+    for (int r = 0; r < world; ++r) {
+      const ArgminRecord *rec = reinterpret_cast<const ArgminRecord *>(records + r * stride);
+      if (rec->min_index != 0x7fffffff && rec->min_cost < min_cost) min_cost = rec->min_cost, min_idx = rec->min_index, min_rank = r;
+      if (rec->owns_incumbent) inc_cost = rec->incumbent_cost, have_inc = true;
+      if (r == 0) cost0 = rec->cost_agent0;
+    }
+    if (min_rank < 0) min_cost = cost0;  // no cost below DBL_MAX: index 0 (:335-342)
+    bool take = true;
+    int result = min_idx;
+    if (best->present && have_inc) {
+      if (!(min_cost < 0.9 * inc_cost)) take = false, result = best->id - 1;
+    }
+    out->argmin_index = min_idx, out->argmin_cost = min_cost, out->incumbent_changed = take;
+    out->best_index = result, out->best_cost = take ? min_cost : inc_cost;
+    if (take) best->present = 1, best->id = min_idx + 1, best->type = agent_type_of_index(min_idx);
+    s_take = take, s_min_rank = min_rank < 0 ? 0 : min_rank;
+  }
+  __syncthreads();
+  if (s_take) {
+    const double *row = reinterpret_cast<const double *>(records + s_min_rank * stride + sizeof(ArgminRecord));
+    for (int i = threadIdx.x; i < n_obs * 3; i += blockDim.x) best_random[i] = row[i];
   }
 }
 

@@ -31,7 +31,7 @@ class PmafError(RuntimeError):
 
 
 class Counters(C.Structure):
-    _fields_ = [("kernel_launches", C.c_uint64), ("rollouts", C.c_uint64), ("agent_steps", C.c_uint64), ("agent_steps_total", C.c_uint64),
+    _fields_ = [("kernel_launches", C.c_uint64), ("collectives", C.c_uint64), ("rollouts", C.c_uint64), ("agent_steps", C.c_uint64), ("agent_steps_total", C.c_uint64),
                 ("last_rollout_ms", C.c_double), ("rollout_ms_total", C.c_double), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("lanes_per_agent", C.c_int), ("block_threads", C.c_int),
                 ("grid_blocks", C.c_int), ("smem_bytes", C.c_int)]
@@ -39,7 +39,7 @@ class Counters(C.Structure):
 
 # every symbol include/pmaf.h declares (tests check that the library exports all of them)
 API_SYMBOLS = [
-    "pmaf_last_error", "pmaf_version", "pmaf_create", "pmaf_destroy", "pmaf_set_shard", "pmaf_set_nccl_comm",
+    "pmaf_last_error", "pmaf_version", "pmaf_create", "pmaf_destroy", "pmaf_set_shard", "pmaf_nccl_unique_id", "pmaf_nccl_init", "pmaf_set_nccl_comm",
     "pmaf_init", "pmaf_seed_random_vecs", "pmaf_set_random_vecs", "pmaf_get_random_vecs",
     "pmaf_set_initial_position", "pmaf_set_real_position", "pmaf_start_prediction", "pmaf_stop_prediction",
     "pmaf_evaluate_agents", "pmaf_move_real_agent", "pmaf_reset_agents", "pmaf_tick", "pmaf_get_num_agents",
@@ -82,6 +82,8 @@ def load_library():
     lib.pmaf_destroy.argtypes = [H]
     lib.pmaf_set_shard.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.pmaf_set_nccl_comm.argtypes = [H, C.c_void_p]
+    lib.pmaf_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.pmaf_nccl_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     lib.pmaf_init.argtypes = [H, _dp, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                               _dp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_double]
     lib.pmaf_seed_random_vecs.argtypes = [H, C.c_uint64]
