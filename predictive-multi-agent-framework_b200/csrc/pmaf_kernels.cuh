@@ -266,14 +266,19 @@ PMAF_HDT int nearest_other_obstacle(const G &g, const Obs &obs, int n_field, int
 //   outputs (identical in every lane of the group): force = sum of curr_force in obstacle order,
 //   min_d = min over non-skipped candidates of dist_obs (+inf if none),
 //   closest_d / closest_i = first obstacle with the smallest dist_obs < shell (closest_i < 0 if none).
+//   STATIC_VEL: every obstacle velocity is zero, so rel_vel == v for all of them (v - 0 is v,
+//   bit for bit) and its norm / unit vector are computed once per step by the caller's values
+//   zv = v.v, vn = sqrt(zv).
+//   ghat = normalized(goal - p), from the caller (it already holds |goal - p|).
 #pragma nv_exec_check_disable
-template <class G, class Obs, class Known>
+template <bool STATIC_VEL, class G, class Obs, class Known>
 PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t *cand, int n_cand, int type, v3 p,
-                         v3 v, v3 goal, double shell, double k_circ, const Known &known, double *rot_row,
-                         const double *random_row, v3 &force, double &min_d, double &closest_d, int &closest_i) {
+                         v3 v, double zv, double vn, v3 goal, v3 ghat, double shell, double k_circ,
+                         const Known &known, double *rot_row, const double *random_row, v3 &force, double &min_d,
+                         double &closest_d, int &closest_i) {
   constexpr int LPA = G::kLanes;
-  const v3 goal_vec = sub3(goal, p);
-  const v3 ghat = normalized3(goal_vec);
+  v3 nv_static = mk3(0.0, 0.0, 0.0);
+  if (STATIC_VEL && vn != 0) nv_static = div3(v, vn);
   const bool needs_nn = type == OBSTACLE_HEURISTIC || type == GOAL_OBSTACLE_HEURISTIC;
   force = mk3(0.0, 0.0, 0.0);
   double lmin = (double)INFINITY;
@@ -290,7 +295,7 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     if (active) {
       oi = obs.pos(i);
       const v3 rov = sub3(oi, p);
-      rel = sub3(v, obs.vel(i));
+      rel = STATIC_VEL ? v : sub3(v, obs.vel(i));
       const double z = dot3(rov, rov);
       const double n = sqrt(z);
       to_obs = normalized_zn(rov, z, n);
@@ -335,10 +340,10 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
       } else {
         rot_i = ld3(rot_row + 3 * i);
       }
-      const double zr = dot3(rel, rel);
-      const double vel_norm = sqrt(zr);
+      const double zr = STATIC_VEL ? zv : dot3(rel, rel);
+      const double vel_norm = STATIC_VEL ? vn : sqrt(zr);
       if (vel_norm != 0) {  // :98
-        const v3 nv = div3(rel, vel_norm);
+        const v3 nv = STATIC_VEL ? nv_static : div3(rel, vel_norm);
         const v3 nv_eigen = zr > 0.0 ? nv : rel;
         const v3 current = current_vector(type, p, goal, to_obs, nv_eigen, rot_i);
         f = circ_force_term(k_circ, dist_obs, nv, current);
@@ -360,10 +365,5 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
   closest_d = lcd;
   closest_i = lci == 0x7fffffff ? -1 : lci;
 }
-
-// One step of cfPrediction's loop body (cf_agent.cpp:312-326) given the field pass results.
-struct StepGains {
-  double k_attr, k_circ, k_repel, k_damp;
-};
 
 }  // namespace pmaf

@@ -138,6 +138,67 @@ PMAF_HD double exp_glibc(double x) {
   return fma(scale, tmp, scale);
 }
 
+// ---- comparing a norm with a constant without taking the square root ---------------------------------
+// sqrt is monotonic and correctly rounded, so "sqrt(z) < c" can be decided on z whenever z is not
+// within a few ulps of c*c; only then is the square root evaluated. The decision is always the one
+// the reference's `v.norm() < c` makes (NaN falls through to the exact comparison).
+struct SqThr {
+  double lo, hi, c;
+};
+PMAF_HD SqThr make_thr(double c) {
+  SqThr t;
+  t.c = c;
+  if (c > 0.0) {
+    const double c2 = c * c;
+    t.lo = c2 * (1.0 - 1e-15), t.hi = c2 * (1.0 + 1e-15);
+  } else {  // c <= 0 or NaN: always take the exact path
+    t.lo = -(double)INFINITY, t.hi = (double)INFINITY;
+  }
+  return t;
+}
+PMAF_HD bool norm_lt(double z, const SqThr &t) {  // sqrt(z) < c
+  if (z < t.lo) return true;
+  if (z > t.hi) return false;
+  return sqrt(z) < t.c;
+}
+PMAF_HD bool norm_gt(double z, const SqThr &t) {  // sqrt(z) > c
+  if (z > t.hi) return true;
+  if (z < t.lo) return false;
+  return sqrt(z) > t.c;
+}
+
+// Per-agent values the reference recomputes identically every step (same operands, same operation:
+// hoisting them changes nothing bitwise).
+struct AgentConsts {
+  double k_attr, k_circ, k_repel, k_damp;
+  double attr_ratio;   // k_attr / k_damp              (attractorForce :189)
+  double inv_shell;    // 1.0 / detect_shell_rad_      (repelForce :176)
+  double half_vmax;    // 0.5 * vel_max_               (gate :288)
+  double vmax90;       // vel_max_ - 0.1 * vel_max_    (attractorForceScaling :216)
+  double shell, vel_max, approach_dist, mass;
+  bool unit_mass;      // force_ / 1.0 == force_ exactly
+};
+PMAF_HD AgentConsts make_agent_consts(double k_attr, double k_circ, double k_repel, double k_damp, double shell,
+                                      double vel_max, double approach_dist, double mass) {
+  AgentConsts c;
+  c.k_attr = k_attr, c.k_circ = k_circ, c.k_repel = k_repel, c.k_damp = k_damp;
+  c.attr_ratio = k_attr / k_damp;
+  c.inv_shell = 1.0 / shell;
+  c.half_vmax = 0.5 * vel_max;
+  c.vmax90 = vel_max - 0.1 * vel_max;
+  c.shell = shell, c.vel_max = vel_max, c.approach_dist = approach_dist, c.mass = mass;
+  c.unit_mass = mass == 1.0;
+  return c;
+}
+
+// `if (current.norm() < 1e-10) current << 0,0,1; current.normalize();` with one square root
+PMAF_HD v3 normalized_or_z(v3 a) {
+  const double z = dot3(a, a);
+  const double n = sqrt(z);
+  if (n < 1e-10) return mk3(0.0, 0.0, 1.0);  // (0,0,1).normalize() is (0,0,1)
+  return z > 0.0 ? div3(a, n) : a;
+}
+
 // ---- rotation vectors (calculateRotationVector) ------------------------------------------------
 // to_obs = normalized(o_i - p), the same value circForce already formed for its skip test.
 
@@ -176,14 +237,10 @@ PMAF_HD v3 rot_goal_obstacle(v3 p, v3 goal, v3 to_obs, v3 o_i, v3 o_c) {
 PMAF_HD v3 current_vector(int type, v3 p, v3 goal, v3 to_obs, v3 nv_eigen, v3 rot_i) {
   if (type == GOAL_HEURISTIC) {  // :389-406
     v3 goal_vec = sub3(goal, p);
-    v3 current = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
-    if (norm3(current) < 1e-10) current = mk3(0.0, 0.0, 1.0);
-    return normalized3(current);
+    return normalized_or_z(sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec))));
   }
   if (type == VEL_HEURISTIC) {  // :520-537
-    v3 current = sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs)));
-    if (norm3(current) < 1e-10) current = mk3(0.0, 0.0, 1.0);
-    return normalized3(current);
+    return normalized_or_z(sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs))));
   }
   // OBSTACLE :414-426, GOAL_OBSTACLE :463-475, RANDOM :545-557, HAD :585-597
   return normalized3(cross3(to_obs, rot_i));
@@ -196,59 +253,67 @@ PMAF_HD v3 circ_force_term(double k_circ, double dist_obs, v3 nv, v3 current) {
 
 // ---- scalar parts of one step ----------------------------------------------------------------------
 // gate of cfPlanner / cfPrediction, :287-289 / :315-317 / :352-354
-PMAF_HD bool field_gate_open(double dist_goal, v3 p, v3 v, v3 init_pos, double approach_dist, double vel_max) {
-  return !(dist_goal < approach_dist || (norm3(v) < 0.5 * vel_max && norm3(sub3(p, init_pos)) < 0.2));
+// dist_goal = |goal - p|, vn = |v| (both needed again later in the step)
+PMAF_HD bool field_gate_open(double dist_goal, double vn, v3 p, v3 init_pos, const AgentConsts &c) {
+  if (dist_goal < c.approach_dist) return false;
+  if (!(vn < c.half_vmax)) return true;
+  const v3 d = sub3(p, init_pos);
+  return !norm_lt(dot3(d, d), make_thr(0.2));
 }
 
 // repelForce :159-181 on the sentinel (last obstacle); rsum = rad_ + sentinel radius.
-PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, double rsum, double shell, double k_repel) {
-  v3 dv = sub3(p, o_s);
-  double z = dot3(dv, dv);
-  double n = sqrt(z);
-  double d = clamp_dist(n - rsum);
+PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, double rsum, const AgentConsts &c) {
+  const v3 dv = sub3(p, o_s);
+  const double z = dot3(dv, dv);
   v3 repel = mk3(0.0, 0.0, 0.0);
-  if (d < shell) {
-    v3 u = normalized_zn(dv, z, n);
-    double s1 = 1.0 / d - 1.0 / shell;
-    double s2 = d * d;
-    repel = mk3(k_repel * u.x * s1 / s2, k_repel * u.y * s1 / s2, k_repel * u.z * s1 / s2);
+  // out of the shell for sure (absolute margin 1e-9 >> rounding of n and n - rsum): skip the sqrt
+  const double far = (c.shell + rsum) + 1e-9;
+  if (!(z > far * far * (1.0 + 1e-15))) {
+    const double n = sqrt(z);
+    const double d = clamp_dist(n - rsum);
+    if (d < c.shell) {
+      const v3 u = normalized_zn(dv, z, n);
+      const double s1 = 1.0 / d - c.inv_shell;
+      const double s2 = d * d;
+      repel = mk3(c.k_repel * u.x * s1 / s2, c.k_repel * u.y * s1 / s2, c.k_repel * u.z * s1 / s2);
+    }
   }
-  v3 total = add3(mk3(0.0, 0.0, 0.0), repel);  // total_repel_force += repel_force (:179)
+  const v3 total = add3(mk3(0.0, 0.0, 0.0), repel);  // total_repel_force += repel_force (:179)
   return add3(force, total);
 }
 
 // attractorForce :183-193
-PMAF_HD v3 add_attractor_force(v3 force, v3 goal_vec, v3 v, double k_attr, double k_damp, double k_goal_scale,
-                               double vel_max) {
-  if (k_attr == 0.0) return force;
-  v3 vel_des = mul3(goal_vec, k_attr / k_damp);
-  double lim = vel_max / norm3(vel_des);
-  double scale_lim = lim < 1.0 ? lim : 1.0;  // std::min(1.0, lim)
+PMAF_HD v3 add_attractor_force(v3 force, v3 goal_vec, v3 v, double k_goal_scale, const AgentConsts &c) {
+  if (c.k_attr == 0.0) return force;
+  v3 vel_des = mul3(goal_vec, c.attr_ratio);
+  const double lim = c.vel_max / norm3(vel_des);
+  const double scale_lim = lim < 1.0 ? lim : 1.0;  // std::min(1.0, lim)
   vel_des = mul3(vel_des, scale_lim);
-  return add3(force, mul3(sub3(vel_des, v), k_goal_scale * k_damp));
+  return add3(force, mul3(sub3(vel_des, v), k_goal_scale * c.k_damp));
 }
 
 // tail of attractorForceScaling :212-226 once the closest in-shell obstacle (distance
-// closest_d, position o_c) is known
-PMAF_HD double attractor_scaling(v3 goal_vec, v3 p, v3 v, double vel_max, double shell, double closest_d, v3 o_c) {
-  if (dot3(goal_vec, v) <= 0.0 && norm3(v) < vel_max - 0.1 * vel_max && norm3(goal_vec) > 0.15) return 0.0;
-  double w1 = 1 - exp_glibc(-sqrt(closest_d) / shell);
-  v3 rov = sub3(o_c, p);
-  double w2 = 1 - (dot3(goal_vec, rov) / (norm3(goal_vec) * norm3(rov)));
+// closest_d, position o_c) is known; dist_goal = |goal_vec|, vn = |v|
+PMAF_HD double attractor_scaling(v3 goal_vec, double dist_goal, v3 p, v3 v, double vn, const AgentConsts &c,
+                                 double closest_d, v3 o_c) {
+  if (dot3(goal_vec, v) <= 0.0 && vn < c.vmax90 && dist_goal > 0.15) return 0.0;
+  const double w1 = 1 - exp_glibc(-sqrt(closest_d) / c.shell);
+  const v3 rov = sub3(o_c, p);
+  double w2 = 1 - (dot3(goal_vec, rov) / (dist_goal * norm3(rov)));
   w2 = w2 * w2;
   return w1 * w2;
 }
 
 // updatePositionAndVelocity :253-268
-PMAF_HD void integrate_step(v3 force, double mass, double dt, double vel_max, v3 &p, v3 &v) {
-  v3 acc = div3(force, mass);
-  double acc_norm = norm3(acc);
-  if (acc_norm > 13.0) acc = mul3(acc, 13.0 / acc_norm);
-  v3 np = mk3((p.x + 0.5 * acc.x * dt * dt) + v.x * dt, (p.y + 0.5 * acc.y * dt * dt) + v.y * dt,
-              (p.z + 0.5 * acc.z * dt * dt) + v.z * dt);
+PMAF_HD void integrate_step(v3 force, double dt, const AgentConsts &c, v3 &p, v3 &v) {
+  v3 acc = c.unit_mass ? force : div3(force, c.mass);
+  const double zacc = dot3(acc, acc);
+  if (norm_gt(zacc, make_thr(13.0))) acc = mul3(acc, 13.0 / sqrt(zacc));
+  const v3 np = mk3((p.x + 0.5 * acc.x * dt * dt) + v.x * dt, (p.y + 0.5 * acc.y * dt * dt) + v.y * dt,
+                    (p.z + 0.5 * acc.z * dt * dt) + v.z * dt);
   v = add3(v, mul3(acc, dt));
-  double vel_norm = norm3(v);
-  if (vel_norm > vel_max) v = mul3(v, vel_max / vel_norm);
+  const double vel_norm = norm3(v);
+  if (vel_norm > c.vel_max) v = mul3(v, c.vel_max / vel_norm);
   p = np;
 }
 

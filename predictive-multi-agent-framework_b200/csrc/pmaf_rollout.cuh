@@ -20,50 +20,55 @@ __host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, i
 // One integration step of one agent (loop body of cfPrediction, cf_agent.cpp:312-326).
 // Returns the new position in p / velocity in v; updates min_obs.
 #pragma nv_exec_check_disable
-template <class G>
+template <bool STATIC_VEL, class G>
 PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
-                         const KnownBits &known, int type, const StepGains &k, v3 init_pos, double *rot_row,
-                         const double *random_row, double dist_goal, v3 &p, v3 &v, double &min_obs) {
+                         const KnownBits &known, int type, const AgentConsts &c, v3 init_pos, double *rot_row,
+                         const double *random_row, v3 goal_vec, double zg, double dist_goal, v3 &p, v3 &v,
+                         double &min_obs) {
   constexpr int LPA = G::kLanes;
   const v3 goal = ld3(P.goal);
   const int n_field = P.n_obs - 1;  // the sentinel is excluded from the field loops (:75)
   v3 force = mk3(0.0, 0.0, 0.0);    // resetForce()
   double k_goal_scale = 1.0;
-  if (field_gate_open(dist_goal, p, v, init_pos, P.approach_dist, P.vel_max)) {
+  const double zv = dot3(v, v);
+  const double vn = sqrt(zv);
+  if (field_gate_open(dist_goal, vn, p, init_pos, c)) {
     // ---- broad phase: fp32 sphere test, ordered compaction of candidate indices ----
     const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
     const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
     int n_cand = 0;
     for (int base = 0; base < n_field; base += LPA) {
       const int i = base + g.gl;
-      bool c = false;
+      bool cnd = false;
       if (i < n_field) {
         const float4 b = bp[i];
         const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
-        c = dx * dx + dy * dy + dz * dz < b.w;
+        cnd = dx * dx + dy * dy + dz * dz < b.w;
       }
-      const unsigned m = g.ballot(c);
-      if (c) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
+      const unsigned m = g.ballot(cnd);
+      if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
       n_cand += PMAF_POPC(m);
     }
-    g.sync();
-    // ---- narrow phase ----
-    double min_d, closest_d;
-    int closest_i;
-    field_pass(g, obs, n_field, cand, n_cand, type, p, v, goal, P.shell, k.k_circ, known, rot_row,
-                    random_row, force, min_d, closest_d, closest_i);
-    if (min_d < min_obs) min_obs = min_d;
-    if (norm3(force) > 1e-5) {  // :319-321
-      k_goal_scale = closest_i < 0 ? 1.0
-                                   : attractor_scaling(sub3(goal, p), p, v, P.vel_max, P.shell, closest_d,
-                                                       obs.pos(closest_i));
+    if (n_cand > 0) {
+      g.sync();
+      // ---- narrow phase ----
+      const v3 ghat = normalized_zn(goal_vec, zg, dist_goal);  // goal_vec.normalized() (:79)
+      double min_d, closest_d;
+      int closest_i;
+      field_pass<STATIC_VEL>(g, obs, n_field, cand, n_cand, type, p, v, zv, vn, goal, ghat, c.shell, c.k_circ, known,
+                             rot_row, random_row, force, min_d, closest_d, closest_i);
+      if (min_d < min_obs) min_obs = min_d;
+      if (norm_gt(dot3(force, force), make_thr(1e-5))) {  // :319-321
+        k_goal_scale =
+            closest_i < 0 ? 1.0 : attractor_scaling(goal_vec, dist_goal, p, v, vn, c, closest_d, obs.pos(closest_i));
+      }
+      g.sync();  // cand[] is rewritten by the next step's broad phase
     }
-    g.sync();  // cand[] is rewritten by the next step's broad phase
   }
   const int s = P.n_obs - 1;
-  force = add_repel_force(force, p, obs.pos(s), obs.rsum(s), P.shell, k.k_repel);
-  force = add_attractor_force(force, sub3(goal, p), v, k.k_attr, k.k_damp, k_goal_scale, P.vel_max);
-  integrate_step(force, P.mass, P.pred_dt, P.vel_max, p, v);
+  force = add_repel_force(force, p, obs.pos(s), obs.rsum(s), c);
+  force = add_attractor_force(force, goal_vec, v, k_goal_scale, c);
+  integrate_step(force, P.pred_dt, c, p, v);
 }
 
 // Rollout of every agent to termination. Each group continues ITS agent from the agent's current
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
   v3 p = mk3(0, 0, 0), v = p, init_pos = p;
   double min_obs = 0, path_len = 0, ws_cost = 0;
   int n_path = 0, type = 0;
-  StepGains k = {0, 0, 0, 0};
+  AgentConsts k = make_agent_consts(0, 0, 0, 1, P.shell, P.vel_max, P.approach_dist, P.mass);
   double *rot_row = nullptr;
   const double *random_row = nullptr;
   if (have_agent) {
@@ -116,7 +121,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
     n_path = P.n_path[a];
     type = agent_type_of_index(P.first_agent + a);
     const int ga = P.first_agent + a;  // gains are indexed by GLOBAL agent index
-    k.k_attr = P.k_attr[ga], k.k_circ = P.k_circ[ga], k.k_repel = P.k_repel[ga], k.k_damp = P.k_damp[ga];
+    k = make_agent_consts(P.k_attr[ga], P.k_circ[ga], P.k_repel[ga], P.k_damp[ga], P.shell, P.vel_max,
+                          P.approach_dist, P.mass);
     rot_row = P.rot + (size_t)a * P.n_obs * 3;
     random_row = P.random_vecs + (size_t)a * P.n_obs * 3;
     for (int w = g.gl; w < P.known_words; w += LPA) known.w[w] = P.known[(size_t)a * P.known_words + w];
@@ -143,11 +149,13 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
 
   for (;;) {
     if (alive) {
-      const double dist_goal = norm3(sub3(goal, p));
+      const v3 goal_vec = sub3(goal, p);
+      const double zg = dot3(goal_vec, goal_vec);
+      const double dist_goal = sqrt(zg);
       if (dist_goal > 0.1 && n_path < P.max_steps) {  // :310-311
         const v3 prev = p;
-        agent_step(g, P, obs, bp, cand, known, type, k, init_pos, rot_row, random_row, dist_goal, p, v,
-                        min_obs);
+        agent_step<!DYNAMIC>(g, P, obs, bp, cand, known, type, k, init_pos, rot_row, random_row, goal_vec, zg,
+                             dist_goal, p, v, min_obs);
         path_len += norm3(sub3(p, prev));  // getPathLength term (:29)
         if (P.fused_valid) ws_cost = add_workspace_cost(ws_cost, p, P.fused_cost.ws, P.fused_cost.k_workspace);
         if (g.gl == 0) st3(path_row + (size_t)n_path * 3, p);
@@ -460,8 +468,8 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   known.b = R.known;
   int aid = R.agent_id;
   if (aid < 0) aid = R.eval->best_index;
-  StepGains k;
-  k.k_attr = P.k_attr[aid], k.k_circ = P.k_circ[aid], k.k_repel = P.k_repel[aid], k.k_damp = P.k_damp[aid];
+  const AgentConsts k = make_agent_consts(P.k_attr[aid], P.k_circ[aid], P.k_repel[aid], P.k_damp[aid], P.shell,
+                                          P.vel_max, P.approach_dist, P.mass);
   const int type = R.best->type;
   const v3 goal = ld3(R.goal);
   const v3 init_pos = ld3(R.real->init_pos);
@@ -471,22 +479,26 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   for (int s = 0; s < R.steps; ++s) {
     force = mk3(0.0, 0.0, 0.0);
     double k_goal_scale = 1.0;
-    const double dist_goal = norm3(sub3(goal, p));
-    if (field_gate_open(dist_goal, p, v, init_pos, P.approach_dist, P.vel_max)) {
+    const v3 goal_vec = sub3(goal, p);
+    const double zg = dot3(goal_vec, goal_vec);
+    const double dist_goal = sqrt(zg);
+    const double zv = dot3(v, v);
+    const double vn = sqrt(zv);
+    if (field_gate_open(dist_goal, vn, p, init_pos, k)) {
       double min_d, closest_d;
       int closest_i;
-      field_pass(g, obs, n_field, nullptr, n_field, type, p, v, goal, P.shell, k.k_circ, known, R.rot,
-                     R.best_random, force, min_d, closest_d, closest_i);
-      if (norm3(force) > 1e-5) {
-        k_goal_scale = closest_i < 0 ? 1.0
-                                     : attractor_scaling(sub3(goal, p), p, v, P.vel_max, P.shell, closest_d,
-                                                         obs.pos(closest_i));
+      const v3 ghat = normalized_zn(goal_vec, zg, dist_goal);
+      field_pass<false>(g, obs, n_field, nullptr, n_field, type, p, v, zv, vn, goal, ghat, P.shell, k.k_circ, known,
+                        R.rot, R.best_random, force, min_d, closest_d, closest_i);
+      if (norm_gt(dot3(force, force), make_thr(1e-5))) {
+        k_goal_scale =
+            closest_i < 0 ? 1.0 : attractor_scaling(goal_vec, dist_goal, p, v, vn, k, closest_d, obs.pos(closest_i));
       }
       g.sync();
     }
-    force = add_repel_force(force, p, obs.pos(R.n_obs - 1), obs.rsum(R.n_obs - 1), P.shell, k.k_repel);
-    force = add_attractor_force(force, sub3(goal, p), v, k.k_attr, k.k_damp, k_goal_scale, P.vel_max);
-    integrate_step(force, P.mass, R.delta_t, P.vel_max, p, v);
+    force = add_repel_force(force, p, obs.pos(R.n_obs - 1), obs.rsum(R.n_obs - 1), k);
+    force = add_attractor_force(force, goal_vec, v, k_goal_scale, k);
+    integrate_step(force, R.delta_t, k, p, v);
     if (g.gl == 0) st3(R.path_out + 3 * s, p);
   }
   if (g.gl == 0 && R.steps > 0) {

@@ -42,16 +42,23 @@ extern "C" int hoststep_rollout(int n_obs, const double *obs_pos, const double *
   KnownBits known;
   known.w = words.data();
   HostGroup g;
-  StepGains k{k_attr, k_circ, k_repel, k_damp};
+  const AgentConsts k = make_agent_consts(k_attr, k_circ, k_repel, k_damp, shell, vmax, approach, mass);
   v3 p = ld3(p0), v = ld3(v0);
   const v3 gl = ld3(goal), ip = ld3(init_pos);
   double min_obs = min_obs0, path_len = 0.0;
   int n_path = *n_path_io;
   for (;;) {
-    const double dist_goal = norm3(sub3(gl, p));
+    const v3 goal_vec = sub3(gl, p);
+    const double zg = dot3(goal_vec, goal_vec);
+    const double dist_goal = sqrt(zg);
     if (!(dist_goal > 0.1 && n_path < H)) break;
     const v3 prev = p;
-    agent_step(g, P, obs, bp.data(), cand.data(), known, type, k, ip, rot_io, random_vecs, dist_goal, p, v, min_obs);
+    if (dynamic)
+      agent_step<false>(g, P, obs, bp.data(), cand.data(), known, type, k, ip, rot_io, random_vecs, goal_vec, zg,
+                        dist_goal, p, v, min_obs);
+    else
+      agent_step<true>(g, P, obs, bp.data(), cand.data(), known, type, k, ip, rot_io, random_vecs, goal_vec, zg,
+                       dist_goal, p, v, min_obs);
     path_len += norm3(sub3(p, prev));
     st3(path + 3 * n_path, p);
     ++n_path;
