@@ -220,6 +220,11 @@ int pmaf_flush_l2(pmaf_planner *p);
 /* Measured FP64 FMA-pipe peak of the device (dependent DFMA chains on every SM), in TFLOP/s:
  * the denominator of the FP-issue roofline of the rollout kernel. */
 int pmaf_measure_fp64_peak(pmaf_planner *p, double *tflops);
+/* Self-test of the kernels' branch-free sqrt / division (FastMath, csrc/pmaf_math.cuh) against CUDA's
+ * IEEE built-ins on ~`samples` random and adversarial operands: out = { sqrt mismatches, division
+ * mismatches, shared-reciprocal vector division mismatches, operands rejected by the range check,
+ * comparisons made }. Any mismatch is a bug. */
+int pmaf_selftest_math(pmaf_planner *p, uint64_t samples, uint64_t seed, uint64_t out[5]);
 
 #ifdef __cplusplus
 }

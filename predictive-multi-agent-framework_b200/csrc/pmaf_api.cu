@@ -680,7 +680,7 @@ template <int LPA>
 static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, bool dynamic) {
   const int groups = block / LPA;
   const int grid = (p->A + groups - 1) / groups;
-  const size_t smem = rollout_smem_bytes(p->img, groups, p->known_words);
+  const size_t smem = rollout_smem_bytes(p->img, groups, LPA, p->known_words);
   REQUIRE(smem <= 227 * 1024, PMAF_ERR_ARG, "rollout needs %zu B of shared memory (> 227 KB): too many obstacles",
           smem);
   auto kern = dynamic ? rollout_kernel<LPA, true> : rollout_kernel<LPA, false>;
@@ -1188,5 +1188,106 @@ extern "C" int pmaf_measure_fp64_peak(pmaf_planner *p, double *tflops) {
   }
   out.release();
   *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best_ms * 1e-3) / 1e12;
+  return 0;
+}
+
+// ---- FastMath self-test ---------------------------------------------------------------------------------------
+namespace pmaf {
+__device__ __forceinline__ unsigned long long xorshift(unsigned long long &s) {
+  s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+  return s;
+}
+__device__ __forceinline__ double random_double(unsigned long long &s, int emin, int emax, bool allow_negative) {
+  const unsigned long long mant = xorshift(s) & ((1ull << 52) - 1);
+  const int e = emin + (int)(xorshift(s) % (unsigned long long)(emax - emin + 1));
+  const unsigned long long sign = allow_negative ? (xorshift(s) & 1ull) << 63 : 0ull;
+  return __longlong_as_double((long long)(sign | ((unsigned long long)(e + 1023) << 52) | mant));
+}
+// out[0] sqrt mismatches, [1] div mismatches, [2] div3 mismatches, [3] samples with the range flag raised,
+// [4] samples compared
+__global__ void math_selftest_kernel(unsigned long long seed, int iters, unsigned long long *out) {
+  unsigned long long s = seed * 0x9E3779B97F4A7C15ull + (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0xD1B54A32D192ED03ull + 1;
+  for (int w = 0; w < 8; ++w) xorshift(s);
+  unsigned long long bad_sqrt = 0, bad_div = 0, bad_div3 = 0, flagged = 0, compared = 0;
+  for (int it = 0; it < iters; ++it) {
+    const int kind = it & 7;
+    double a, b;
+    if (kind == 0) {  // generic
+      a = random_double(s, -40, 40, true), b = random_double(s, -40, 40, false);
+    } else if (kind == 1) {  // quotient next to a rounding boundary: a = RN(b * (q + ulp/2)) +- ulp
+      b = random_double(s, -6, 6, false);
+      const double q = random_double(s, -6, 6, false);
+      const double half_ulp = __longlong_as_double(__double_as_longlong(q) + 1) - q;
+      a = fma(b, 0.5 * half_ulp, b * q);
+      const long long adj = (long long)(xorshift(s) % 3) - 1;
+      a = __longlong_as_double(__double_as_longlong(a) + adj);
+    } else if (kind == 2) {  // divisor significand all ones / near a power of two
+      const unsigned long long mant = (xorshift(s) & 1) ? ((1ull << 52) - 1 - (xorshift(s) & 15)) : (xorshift(s) & 15);
+      b = __longlong_as_double((long long)(((unsigned long long)(1023 + (int)(xorshift(s) % 21) - 10) << 52) | mant));
+      a = random_double(s, -10, 10, true);
+    } else if (kind == 3) {  // component of a vector over its norm: |a| <= b
+      b = random_double(s, -14, 4, false);
+      a = b * ((double)(xorshift(s) >> 11) * (1.0 / 9007199254740992.0)) * ((xorshift(s) & 1) ? 1.0 : -1.0);
+    } else if (kind == 4) {  // square root of an exact square and its neighbours
+      const double r = random_double(s, -20, 20, false);
+      const double r26 = __longlong_as_double(__double_as_longlong(r) & ~((1ll << 27) - 1));  // 26-bit r: r*r exact
+      a = r26 * r26;
+      a = __longlong_as_double(__double_as_longlong(a) + (long long)(xorshift(s) % 3) - 1);
+      b = random_double(s, -3, 3, false);
+    } else if (kind == 5) {  // squared norms of metre-scale vectors
+      const double x = random_double(s, -12, 2, true), y = random_double(s, -12, 2, true), z = random_double(s, -12, 2, true);
+      a = (x * x + y * y) + z * z;
+      b = sqrt(a);
+    } else if (kind == 6) {  // operands that must raise the flag
+      const int pick = (int)(xorshift(s) % 6);
+      a = pick == 0 ? 0.0 : pick == 1 ? -1.0 : pick == 2 ? 1e-300 : pick == 3 ? 1e300 : pick == 4 ? __longlong_as_double(0x7ff8000000000000ll) : random_double(s, -2, 2, true);
+      b = pick == 5 ? 0.0 : random_double(s, -2, 2, false);
+    } else {  // wide exponents inside the proven range
+      a = random_double(s, -590, 590, true), b = random_double(s, -295, 295, false);
+    }
+    const double x = fabs(a);
+    {
+      FastMath fm;
+      const double got = fm.sqrt_(x);
+      if (fm.bad()) ++flagged;
+      else if (__double_as_longlong(got) != __double_as_longlong(sqrt(x))) ++bad_sqrt;
+    }
+    {
+      FastMath fm;
+      const double got = fm.div_(a, b);
+      if (fm.bad()) ++flagged;
+      else if (__double_as_longlong(got) != __double_as_longlong(a / b)) ++bad_div;
+    }
+    {
+      FastMath fm;
+      const v3 num = mk3(a, 0.37 * a, -a * 1.9);
+      const v3 got = fm.div3_(num, b);
+      if (fm.bad()) ++flagged;
+      else if (__double_as_longlong(got.x) != __double_as_longlong(num.x / b) ||
+               __double_as_longlong(got.y) != __double_as_longlong(num.y / b) ||
+               __double_as_longlong(got.z) != __double_as_longlong(num.z / b))
+        ++bad_div3;
+    }
+    compared += 3;
+  }
+  atomicAdd(out + 0, bad_sqrt), atomicAdd(out + 1, bad_div), atomicAdd(out + 2, bad_div3);
+  atomicAdd(out + 3, flagged), atomicAdd(out + 4, compared);
+}
+}  // namespace pmaf
+
+extern "C" int pmaf_selftest_math(pmaf_planner *p, uint64_t samples, uint64_t seed, uint64_t out[5]) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  DevBuf<unsigned long long> d;
+  CU(d.resize(5));
+  CU(cudaMemsetAsync(d.p, 0, 5 * sizeof(unsigned long long), p->stream));
+  const int blocks = 148 * 8, threads = 256;
+  const int iters = (int)std::max<uint64_t>(8, samples / ((uint64_t)blocks * threads));
+  if (int rc = launch(p, math_selftest_kernel, dim3(blocks), dim3(threads), 0, (unsigned long long)seed, iters, d.p)) return rc;
+  unsigned long long h[5];
+  CU(cudaMemcpyAsync(h, d.p, sizeof h, cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  for (int i = 0; i < 5; ++i) out[i] = h[i];
+  d.release();
   return 0;
 }

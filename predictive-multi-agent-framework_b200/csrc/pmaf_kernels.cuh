@@ -183,6 +183,21 @@ struct Group {
     }
     return v;
   }
+  // minimum of NON-NEGATIVE doubles (or +inf): their bit patterns order like unsigned integers, so
+  // two redux.sync.min (high word, then low word among the lanes holding the smallest high word)
+  // replace a five-level shuffle tree. Returns the minimum in every lane.
+  __device__ __forceinline__ double min_reduce_nonneg(double v) const {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_min_sync(mask, hi);
+    const unsigned mlo = __reduce_min_sync(mask, hi == mhi ? lo : 0xffffffffu);
+    return __hiloint2double((int)mhi, (int)mlo);
+  }
+  // lexicographic (value, index) minimum for non-negative values, same idea; idx >= 0
+  __device__ __forceinline__ void argmin_reduce_nonneg(double &v, int &idx) const {
+    const double m = min_reduce_nonneg(v);
+    const unsigned mi = __reduce_min_sync(mask, v == m ? (unsigned)idx : 0xffffffffu);
+    v = m, idx = (int)mi;
+  }
   // lexicographic (value, index) minimum: smallest value, lowest index among equals
   __device__ __forceinline__ void argmin_reduce(double &v, int &idx) const {
 #pragma unroll
@@ -205,6 +220,8 @@ struct HostGroup {
   PMAF_HDT void sync() const {}
   PMAF_HDT double min_reduce(double v) const { return v; }
   PMAF_HDT void argmin_reduce(double &, int &) const {}
+  PMAF_HDT double min_reduce_nonneg(double v) const { return v; }
+  PMAF_HDT void argmin_reduce_nonneg(double &, int &) const {}
 };
 
 // ---- obstacle accessors ---------------------------------------------------------------------------------
@@ -260,110 +277,178 @@ PMAF_HDT int nearest_other_obstacle(const G &g, const Obs &obs, int n_field, int
   return best_i == 0x7fffffff ? 0 : best_i;
 }
 
+// What one lane learns about its candidate in one chunk of the narrow phase; nothing is written to
+// memory until the whole group's evaluation is known to be in the arithmetic policy's proven range.
+struct CandEval {
+  v3 f, rot_i;
+  double d;        // dist_obs (clamped), +inf for an idle lane
+  double kgs;      // attractorForceScaling's value IF this obstacle turns out to be the closest one
+  bool counts_min, in_shell, first_seen, contributes;
+};
+
+// circForce loop body for obstacle i (cf_agent.cpp:76-105), pure: reads p, v, the obstacle, its known
+// flag and stored rotation vector; returns the force term and what has to be committed.
+//   STATIC_VEL: every obstacle velocity is zero, so rel_vel == v for all of them (v - 0 is v, bit
+//   for bit); zv = v.v, vn = sqrt(zv) and nv_static = v / vn come from the caller, once per step.
+//   ghat = normalized(goal - p) from the caller (it already holds |goal - p|).
+// Every in-shell lane also evaluates the tail of attractorForceScaling (:212-226) for ITS obstacle:
+// the chain (sqrt, division, exp; sqrt, division) is independent of the current-vector chain, so the
+// two interleave, and after the closest-obstacle reduction the winner's value is just broadcast.
+#pragma nv_exec_check_disable
+template <bool STATIC_VEL, class M, class G, class Obs, class Known>
+PMAF_HDT CandEval eval_candidate(M &m, const G &g, const Obs &obs, int n_field, bool active, int i, int type, v3 p,
+                                 v3 v, v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat,
+                                 const AgentConsts &c, const Known &known, const double *rot_row,
+                                 const double *random_row) {
+  CandEval r;
+  r.f = mk3(0.0, 0.0, 0.0), r.rot_i = r.f, r.d = (double)INFINITY, r.kgs = 1.0;
+  r.counts_min = r.in_shell = r.first_seen = r.contributes = false;
+  v3 to_obs = r.f, rel = r.f, oi = r.f;
+  bool is_known = false;
+  if (active) {
+    oi = obs.pos(i);
+    is_known = known.test(i);
+    if (is_known) r.rot_i = ld3(rot_row + 3 * i);  // issued early: the latency hides behind the sqrt / divisions
+    const v3 rov = sub3(oi, p);
+    rel = STATIC_VEL ? v : sub3(v, obs.vel(i));
+    const double z = dot3(rov, rov);
+    const double n = m.sqrt_(z);
+    to_obs = normalized_zn_m(m, rov, z, n);
+    r.d = clamp_dist(n - obs.rsum(i));
+    const bool skip = dot3(to_obs, ghat) < -0.01 && dot3(rov, rel) < -0.01;  // :79-82
+    if (!skip) {
+      r.counts_min = true;           // :86-88
+      r.in_shell = r.d < c.shell;    // :91
+      r.first_seen = r.in_shell && !is_known;
+    }
+  }
+  int nn = 0;
+  if (type == OBSTACLE_HEURISTIC || type == GOAL_OBSTACLE_HEURISTIC) {
+    // group-uniform branch: cooperative nearest-neighbour scans, one per newly detected obstacle
+    unsigned todo = g.ballot(r.first_seen);
+    while (todo) {
+      const int src = PMAF_FFS(todo) - 1;
+      todo &= todo - 1;
+      const int id = g.bcast(i, src);
+      const int found = nearest_other_obstacle(g, obs, n_field, id);
+      if (g.lane == src) nn = found;
+    }
+  }
+  if (r.d < c.shell) {  // candidates of the closest-obstacle search (:201-211), skipped ones included
+    if (r.first_seen) {  // :92-96 (rare: built-in arithmetic)
+      switch (type) {
+        case HAD_HEURISTIC: r.rot_i = rot_had(p, goal, oi); break;
+        case RANDOM_AGENT: r.rot_i = rot_random(p, goal, ld3(random_row + 3 * i)); break;
+        case OBSTACLE_HEURISTIC: r.rot_i = rot_obstacle(to_obs, oi, obs.pos(nn)); break;
+        case GOAL_OBSTACLE_HEURISTIC: r.rot_i = rot_goal_obstacle(p, goal, to_obs, oi, obs.pos(nn)); break;
+        default: r.rot_i = mk3(0.0, 0.0, 1.0); break;  // GOAL :408-412, VEL :539-543
+      }
+    } else if (!is_known) {
+      r.rot_i = mk3(0.0, 0.0, 1.0);  // skipped obstacle: its force is discarded below
+    }
+    // one straight-line block: scaling chain and force chain are independent
+    r.kgs = attractor_scaling(m, goal_vec, sn.dist_goal, p, v, sn.vn, c, r.d, oi);
+    const double zr = STATIC_VEL ? sn.zv : dot3(rel, rel);
+    const double vel_norm = STATIC_VEL ? sn.vn : m.sqrt_(zr);
+    const v3 nv = STATIC_VEL ? nv_static : m.div3_(rel, vel_norm);
+    const v3 nv_eigen = zr > 0.0 ? nv : rel;
+    const v3 current = current_vector(m, type, p, goal, to_obs, nv_eigen, r.rot_i);
+    const v3 f = circ_force_term(m, c.k_circ, r.d, nv, current);
+    if (r.in_shell && vel_norm != 0) {  // :91, :98
+      r.f = f;
+      r.contributes = true;
+    }
+  }
+  return r;
+}
+
+// the same evaluation with the built-in IEEE operations, out of line: taken only when some lane's
+// operands fall outside FastMath's range
+#pragma nv_exec_check_disable
+template <bool STATIC_VEL, class G, class Obs, class Known>
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+    CandEval
+    eval_candidate_exact(const G &g, const Obs &obs, int n_field, bool active, int i, int type, v3 p, v3 v,
+                         v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat, const AgentConsts &c,
+                         const Known &known, const double *rot_row, const double *random_row) {
+  ExactMath em;
+  return eval_candidate<STATIC_VEL>(em, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat, c,
+                                    known, rot_row, random_row);
+}
+
 // CfAgent::circForce / RealCfAgent::circForce (cf_agent.cpp:72-144) over a candidate list, plus the
 // closest-obstacle search of attractorForceScaling (:199-211).
 //   cand == nullptr: candidates are 0..n_cand-1 themselves.
+//   fbuf: per-group staging buffer, 3 * kLanes doubles (shared memory on the GPU).
 //   outputs (identical in every lane of the group): force = sum of curr_force in obstacle order,
-//   min_d = min over non-skipped candidates of dist_obs (+inf if none),
-//   closest_d / closest_i = first obstacle with the smallest dist_obs < shell (closest_i < 0 if none).
-//   STATIC_VEL: every obstacle velocity is zero, so rel_vel == v for all of them (v - 0 is v,
-//   bit for bit) and its norm / unit vector are computed once per step by the caller's values
-//   zv = v.v, vn = sqrt(zv).
-//   ghat = normalized(goal - p), from the caller (it already holds |goal - p|).
+//   min_d = min over non-skipped candidates of dist_obs (+inf if none), has_closest / kgs_closest =
+//   whether an obstacle lies within the shell, and attractorForceScaling's value for the first one
+//   with the smallest dist_obs.
 #pragma nv_exec_check_disable
 template <bool STATIC_VEL, class G, class Obs, class Known>
 PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t *cand, int n_cand, int type, v3 p,
-                         v3 v, double zv, double vn, v3 goal, v3 ghat, double shell, double k_circ,
-                         const Known &known, double *rot_row, const double *random_row, v3 &force, double &min_d,
-                         double &closest_d, int &closest_i) {
+                         v3 v, v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat,
+                         const AgentConsts &c, const Known &known, double *rot_row, const double *random_row,
+                         double *fbuf, v3 &force, double &min_d, bool &has_closest, double &kgs_closest) {
   constexpr int LPA = G::kLanes;
-  v3 nv_static = mk3(0.0, 0.0, 0.0);
-  if (STATIC_VEL && vn != 0) nv_static = div3(v, vn);
-  const bool needs_nn = type == OBSTACLE_HEURISTIC || type == GOAL_OBSTACLE_HEURISTIC;
   force = mk3(0.0, 0.0, 0.0);
   double lmin = (double)INFINITY;
-  double lcd = shell;
+  double lcd = c.shell, lkgs = 1.0;
   int lci = 0x7fffffff;
+  const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
 
   for (int c0 = 0; c0 < n_cand; c0 += LPA) {
-    const int c = c0 + g.gl;
-    const bool active = c < n_cand;
-    const int i = active ? (cand ? (int)cand[c] : c) : 0;
-    bool in_shell = false, first_seen = false;
-    v3 to_obs = mk3(0.0, 0.0, 0.0), rel = mk3(0.0, 0.0, 0.0), oi = mk3(0.0, 0.0, 0.0);
-    double dist_obs = 0.0;
-    if (active) {
-      oi = obs.pos(i);
-      const v3 rov = sub3(oi, p);
-      rel = STATIC_VEL ? v : sub3(v, obs.vel(i));
-      const double z = dot3(rov, rov);
-      const double n = sqrt(z);
-      to_obs = normalized_zn(rov, z, n);
-      const double d = clamp_dist(n - obs.rsum(i));
-      // attractorForceScaling's search ignores the skip test (:201-211)
-      if (d < lcd) lcd = d, lci = i;
-      const bool skip = dot3(to_obs, ghat) < -0.01 && dot3(rov, rel) < -0.01;  // :79-82
-      if (!skip) {
-        if (d < lmin) lmin = d;  // :86-88
-        dist_obs = d;
-        in_shell = d < shell;  // :91
-        first_seen = in_shell && !known.test(i);
-      }
+    const int ci = c0 + g.gl;
+    const bool active = ci < n_cand;
+    const int i = active ? (cand ? (int)cand[ci] : ci) : 0;
+    FastMath fm;
+    CandEval r = eval_candidate<STATIC_VEL>(fm, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal,
+                                            ghat, c, known, rot_row, random_row);
+    if (g.ballot(fm.bad()))
+      r = eval_candidate_exact<STATIC_VEL>(g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat,
+                                           c, known, rot_row, random_row);
+    // ---- commit ----
+    if (r.d < lcd) lcd = r.d, lci = i, lkgs = r.kgs;  // the search ignores the skip test (:201-211)
+    if (r.counts_min && r.d < lmin) lmin = r.d;
+    if (r.first_seen) {
+      st3(rot_row + 3 * i, r.rot_i);
+      known.set(i);
     }
-    int nn = 0;
-    if (needs_nn) {  // group-uniform branch: cooperative nearest-neighbour scans, one per new obstacle
-      unsigned m = g.ballot(first_seen);
-      while (m) {
-        const int src = PMAF_FFS(m) - 1;
-        m &= m - 1;
-        const int id = g.bcast(i, src);
-        const int r = nearest_other_obstacle(g, obs, n_field, id);
-        if (g.lane == src) nn = r;
+    // force_ += curr_force in obstacle order (:106). Candidates are sorted and lanes are in list order,
+    // so the contributions are compacted into the staging buffer by rank and every lane then adds them
+    // up front to back: a chain of dependent adds fed by broadcast loads.
+    const unsigned contrib = g.ballot(r.contributes);
+    if (contrib) {
+      if (r.contributes) {
+        const int rank = PMAF_POPC(contrib & lt_mask);
+        fbuf[3 * rank] = r.f.x, fbuf[3 * rank + 1] = r.f.y, fbuf[3 * rank + 2] = r.f.z;
       }
-    }
-    v3 f = mk3(0.0, 0.0, 0.0);
-    bool contributes = false;
-    if (in_shell) {
-      v3 rot_i;
-      if (first_seen) {  // :92-96
-        switch (type) {
-          case HAD_HEURISTIC: rot_i = rot_had(p, goal, oi); break;
-          case RANDOM_AGENT: rot_i = rot_random(p, goal, ld3(random_row + 3 * i)); break;
-          case OBSTACLE_HEURISTIC:
-            rot_i = n_field + 1 < 2 ? mk3(0.0, 0.0, 1.0) : rot_obstacle(to_obs, oi, obs.pos(nn));
-            break;
-          case GOAL_OBSTACLE_HEURISTIC: rot_i = rot_goal_obstacle(p, goal, to_obs, oi, obs.pos(nn)); break;
-          default: rot_i = mk3(0.0, 0.0, 1.0); break;  // GOAL :408-412, VEL :539-543
-        }
-        st3(rot_row + 3 * i, rot_i);
-        known.set(i);
-      } else {
-        rot_i = ld3(rot_row + 3 * i);
+      g.sync();
+      const int n_contrib = PMAF_POPC(contrib);
+      for (int j = 0; j < n_contrib; ++j) {
+        force.x += fbuf[3 * j], force.y += fbuf[3 * j + 1], force.z += fbuf[3 * j + 2];
       }
-      const double zr = STATIC_VEL ? zv : dot3(rel, rel);
-      const double vel_norm = STATIC_VEL ? vn : sqrt(zr);
-      if (vel_norm != 0) {  // :98
-        const v3 nv = STATIC_VEL ? nv_static : div3(rel, vel_norm);
-        const v3 nv_eigen = zr > 0.0 ? nv : rel;
-        const v3 current = current_vector(type, p, goal, to_obs, nv_eigen, rot_i);
-        f = circ_force_term(k_circ, dist_obs, nv, current);
-        contributes = true;
-      }
-    }
-    // force_ += curr_force in obstacle order (:106): candidates are sorted, lanes are in list order
-    unsigned fm = g.ballot(contributes);
-    while (fm) {
-      const int src = PMAF_FFS(fm) - 1;
-      fm &= fm - 1;
-      force.x += g.bcast(f.x, src);
-      force.y += g.bcast(f.y, src);
-      force.z += g.bcast(f.z, src);
+      g.sync();
     }
   }
-  min_d = g.min_reduce(lmin);
-  g.argmin_reduce(lcd, lci);
-  closest_d = lcd;
-  closest_i = lci == 0x7fffffff ? -1 : lci;
+  // reductions only when they can matter
+  const bool shell_ok = c.shell > 0.0;  // non-negative keys for the integer-ordered reductions
+  if (g.ballot(lmin < (double)INFINITY)) min_d = shell_ok ? g.min_reduce_nonneg(lmin) : g.min_reduce(lmin);
+  else min_d = (double)INFINITY;
+  has_closest = g.ballot(lci != 0x7fffffff) != 0u;
+  kgs_closest = 1.0;
+  if (has_closest) {
+    const int mine = lci;
+    if (shell_ok) g.argmin_reduce_nonneg(lcd, lci);
+    else g.argmin_reduce(lcd, lci);
+    // the lane that evaluated the winning obstacle holds its scaling value
+    const unsigned who = g.ballot(mine == lci);
+    kgs_closest = g.bcast(lkgs, PMAF_FFS(who) - 1);
+  }
 }
 
 }  // namespace pmaf

@@ -77,6 +77,88 @@ PMAF_HD v3 normalized3(v3 a) {
 // std::max(d, 1e-5) (cf_agent.cpp:85): NaN stays NaN
 PMAF_HD double clamp_dist(double d) { return d < 1e-5 ? 1e-5 : d; }
 
+// ---- arithmetic policies ---------------------------------------------------------------------------
+// The reference's x86-64 build rounds every sqrt and division correctly (IEEE). Two ways to get the
+// same bits on the GPU:
+//   ExactMath  CUDA's built-in IEEE sqrt / division. Always right; each one is a MUFU seed, ~8 FMAs
+//              and a range check that branches to a slow-path subroutine — the branches serialise
+//              independent chains, which is what bounds a latency-bound rollout.
+//   FastMath   the same Newton/Goldschmidt refinements with the Markstein final corrections
+//              (residual by FMA, one more FMA), written branch-free; one reciprocal is shared by the
+//              three coefficients of a vector. They are proven only while no intermediate
+//              under/overflows, so every operand is range-checked with two integer instructions on
+//              its exponent field and a failed check raises `flag` instead of branching. The caller
+//              evaluates a whole section (a pure function of registers) with FastMath and re-evaluates
+//              it with ExactMath if the flag is up (zero / tiny / huge / NaN operands: rare).
+//              pmaf_selftest_math compares FastMath with ExactMath on the GPU over random and
+//              adversarial operands (tests/test_gpu_math.py). On the host FastMath is ExactMath.
+struct ExactMath {
+  PMAF_HD double sqrt_(double x) { return sqrt(x); }
+  PMAF_HD double div_(double a, double b) { return a / b; }
+  PMAF_HD v3 div3_(v3 a, double b) { return div3(a, b); }
+  PMAF_HD bool bad() const { return false; }
+};
+
+struct FastMath {
+  unsigned flag;
+  PMAF_HD FastMath() : flag(0u) {}
+  PMAF_HD bool bad() const { return flag != 0u; }
+#if defined(__CUDA_ARCH__)
+  // exponent field of x within [2^lo, 2^hi): also rejects zero, subnormals, negatives, inf, NaN
+  __device__ __forceinline__ void need_range(double x, int lo, int hi) {
+    const unsigned h = (unsigned)__double2hiint(x);
+    flag |= (unsigned)((h - ((unsigned)(1023 + lo) << 20)) >= ((unsigned)(hi - lo) << 20));
+  }
+  __device__ __forceinline__ void need_range_or_zero(double x, int lo, int hi) {
+    const unsigned h = (unsigned)__double2hiint(x) & 0x7fffffffu;
+    flag |= (unsigned)(((h - ((unsigned)(1023 + lo) << 20)) >= ((unsigned)(hi - lo) << 20)) && x != 0.0);
+  }
+  // RN(sqrt(x)) for x in [2^-600, 2^600)
+  __device__ __forceinline__ double sqrt_(double x) {
+    need_range(x, -600, 600);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g), h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g), h = fma(h, r, h);
+    const double d = fma(-g, g, x);  // exact residual
+    return fma(d, h, g);
+  }
+  // reciprocal of b in [2^-300, 2^300), refined to within an ulp
+  __device__ __forceinline__ double rcp_(double b) {
+    need_range(b, -300, 300);
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    return fma(y, e, y);
+  }
+  // RN(a / b) given y ~ 1/b: product, two residual corrections (the second is Markstein's final step)
+  __device__ __forceinline__ double quot_(double a, double b, double y) {
+    need_range_or_zero(a, -600, 600);
+    double q = a * y;
+    double r = fma(-b, q, a);
+    q = fma(r, y, q);
+    r = fma(-b, q, a);
+    q = fma(r, y, q);
+    // b > 0, so the quotient has the numerator's sign; this also restores it on a zero numerator
+    return __hiloint2double((__double2hiint(q) & 0x7fffffff) | (__double2hiint(a) & (int)0x80000000), __double2loint(q));
+  }
+  __device__ __forceinline__ double div_(double a, double b) { return quot_(a, b, rcp_(b)); }
+  __device__ __forceinline__ v3 div3_(v3 a, double b) {
+    const double y = rcp_(b);
+    return mk3(quot_(a.x, b, y), quot_(a.y, b, y), quot_(a.z, b, y));
+  }
+#else
+  double sqrt_(double x) { return sqrt(x); }
+  double div_(double a, double b) { return a / b; }
+  v3 div3_(v3 a, double b) { return div3(a, b); }
+#endif
+};
+
 // ---- exp() of the host libm ------------------------------------------------------------------------
 // attractorForceScaling calls std::exp (:220). CUDA's exp() and glibc's differ in the last bit for a
 // few percent of the arguments, and the rollout amplifies a one-ulp difference through its hard
@@ -176,10 +258,12 @@ struct AgentConsts {
   double half_vmax;    // 0.5 * vel_max_               (gate :288)
   double vmax90;       // vel_max_ - 0.1 * vel_max_    (attractorForceScaling :216)
   double shell, vel_max, approach_dist, mass;
+  double rsum_s;       // rad_ + sentinel radius          (repelForce :168)
+  double repel_far2;   // squared distance beyond which the sentinel is certainly out of the shell
   bool unit_mass;      // force_ / 1.0 == force_ exactly
 };
 PMAF_HD AgentConsts make_agent_consts(double k_attr, double k_circ, double k_repel, double k_damp, double shell,
-                                      double vel_max, double approach_dist, double mass) {
+                                      double vel_max, double approach_dist, double mass, double rsum_s) {
   AgentConsts c;
   c.k_attr = k_attr, c.k_circ = k_circ, c.k_repel = k_repel, c.k_damp = k_damp;
   c.attr_ratio = k_attr / k_damp;
@@ -187,16 +271,34 @@ PMAF_HD AgentConsts make_agent_consts(double k_attr, double k_circ, double k_rep
   c.half_vmax = 0.5 * vel_max;
   c.vmax90 = vel_max - 0.1 * vel_max;
   c.shell = shell, c.vel_max = vel_max, c.approach_dist = approach_dist, c.mass = mass;
+  c.rsum_s = rsum_s;
+  const double far = (shell + rsum_s) + 1e-9;  // absolute margin >> rounding of n and n - rsum
+  c.repel_far2 = far * far * (1.0 + 1e-15);
   c.unit_mass = mass == 1.0;
   return c;
 }
 
-// `if (current.norm() < 1e-10) current << 0,0,1; current.normalize();` with one square root
-PMAF_HD v3 normalized_or_z(v3 a) {
+// Eigen normalized() under a policy. The quotient is formed unconditionally (branch-free) and
+// selected: z == 0 raises FastMath's flag, and ExactMath's 0/0 is discarded by the select.
+template <class M>
+PMAF_HD v3 normalized_m(M &m, v3 a) {
   const double z = dot3(a, a);
-  const double n = sqrt(z);
+  const v3 q = m.div3_(a, m.sqrt_(z));
+  return z > 0.0 ? q : a;
+}
+template <class M>
+PMAF_HD v3 normalized_zn_m(M &m, v3 a, double z, double n) {
+  const v3 q = m.div3_(a, n);
+  return z > 0.0 ? q : a;
+}
+// `if (current.norm() < 1e-10) current << 0,0,1; current.normalize();` with one square root
+template <class M>
+PMAF_HD v3 normalized_or_z(M &m, v3 a) {
+  const double z = dot3(a, a);
+  const double n = m.sqrt_(z);
+  const v3 q = m.div3_(a, n);
   if (n < 1e-10) return mk3(0.0, 0.0, 1.0);  // (0,0,1).normalize() is (0,0,1)
-  return z > 0.0 ? div3(a, n) : a;
+  return z > 0.0 ? q : a;
 }
 
 // ---- rotation vectors (calculateRotationVector) ------------------------------------------------
@@ -234,21 +336,23 @@ PMAF_HD v3 rot_goal_obstacle(v3 p, v3 goal, v3 to_obs, v3 o_i, v3 o_c) {
 
 // ---- current vectors (currentVector) -------------------------------------------------------------
 // rel = relative velocity (the caller passes rel_vel as agent_vel, :100), nv_eigen = rel.normalized()
-PMAF_HD v3 current_vector(int type, v3 p, v3 goal, v3 to_obs, v3 nv_eigen, v3 rot_i) {
+template <class M>
+PMAF_HD v3 current_vector(M &m, int type, v3 p, v3 goal, v3 to_obs, v3 nv_eigen, v3 rot_i) {
   if (type == GOAL_HEURISTIC) {  // :389-406
     v3 goal_vec = sub3(goal, p);
-    return normalized_or_z(sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec))));
+    return normalized_or_z(m, sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec))));
   }
   if (type == VEL_HEURISTIC) {  // :520-537
-    return normalized_or_z(sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs))));
+    return normalized_or_z(m, sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs))));
   }
   // OBSTACLE :414-426, GOAL_OBSTACLE :463-475, RANDOM :545-557, HAD :585-597
-  return normalized3(cross3(to_obs, rot_i));
+  return normalized_m(m, cross3(to_obs, rot_i));
 }
 
 // circular-field force of one in-shell obstacle, :98-104
-PMAF_HD v3 circ_force_term(double k_circ, double dist_obs, v3 nv, v3 current) {
-  return mul3(cross3(nv, cross3(current, nv)), k_circ / (dist_obs * dist_obs));
+template <class M>
+PMAF_HD v3 circ_force_term(M &m, double k_circ, double dist_obs, v3 nv, v3 current) {
+  return mul3(cross3(nv, cross3(current, nv)), m.div_(k_circ, dist_obs * dist_obs));
 }
 
 // ---- scalar parts of one step ----------------------------------------------------------------------
@@ -262,15 +366,13 @@ PMAF_HD bool field_gate_open(double dist_goal, double vn, v3 p, v3 init_pos, con
 }
 
 // repelForce :159-181 on the sentinel (last obstacle); rsum = rad_ + sentinel radius.
-PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, double rsum, const AgentConsts &c) {
+PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, const AgentConsts &c) {
   const v3 dv = sub3(p, o_s);
   const double z = dot3(dv, dv);
   v3 repel = mk3(0.0, 0.0, 0.0);
-  // out of the shell for sure (absolute margin 1e-9 >> rounding of n and n - rsum): skip the sqrt
-  const double far = (c.shell + rsum) + 1e-9;
-  if (!(z > far * far * (1.0 + 1e-15))) {
+  if (!(z > c.repel_far2)) {  // otherwise out of the shell for sure: skip the sqrt
     const double n = sqrt(z);
-    const double d = clamp_dist(n - rsum);
+    const double d = clamp_dist(n - c.rsum_s);
     if (d < c.shell) {
       const v3 u = normalized_zn(dv, z, n);
       const double s1 = 1.0 / d - c.inv_shell;
@@ -283,38 +385,83 @@ PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, double rsum, const AgentConst
 }
 
 // attractorForce :183-193
-PMAF_HD v3 add_attractor_force(v3 force, v3 goal_vec, v3 v, double k_goal_scale, const AgentConsts &c) {
-  if (c.k_attr == 0.0) return force;
+// first half: the velocity-limited desired velocity depends on the position only, so it is formed in
+// the step prologue, off the critical path of the field evaluation
+template <class M>
+PMAF_HD v3 desired_velocity(M &m, v3 goal_vec, const AgentConsts &c) {
   v3 vel_des = mul3(goal_vec, c.attr_ratio);
-  const double lim = c.vel_max / norm3(vel_des);
+  const double lim = m.div_(c.vel_max, m.sqrt_(dot3(vel_des, vel_des)));
   const double scale_lim = lim < 1.0 ? lim : 1.0;  // std::min(1.0, lim)
-  vel_des = mul3(vel_des, scale_lim);
+  return mul3(vel_des, scale_lim);
+}
+PMAF_HD v3 add_attractor_force(v3 force, v3 vel_des, v3 v, double k_goal_scale, const AgentConsts &c) {
+  if (c.k_attr == 0.0) return force;
   return add3(force, mul3(sub3(vel_des, v), k_goal_scale * c.k_damp));
 }
 
 // tail of attractorForceScaling :212-226 once the closest in-shell obstacle (distance
 // closest_d, position o_c) is known; dist_goal = |goal_vec|, vn = |v|
-PMAF_HD double attractor_scaling(v3 goal_vec, double dist_goal, v3 p, v3 v, double vn, const AgentConsts &c,
+template <class M>
+PMAF_HD double attractor_scaling(M &m, v3 goal_vec, double dist_goal, v3 p, v3 v, double vn, const AgentConsts &c,
                                  double closest_d, v3 o_c) {
   if (dot3(goal_vec, v) <= 0.0 && vn < c.vmax90 && dist_goal > 0.15) return 0.0;
-  const double w1 = 1 - exp_glibc(-sqrt(closest_d) / c.shell);
+  const double w1 = 1 - exp_glibc(m.div_(-m.sqrt_(closest_d), c.shell));
   const v3 rov = sub3(o_c, p);
-  double w2 = 1 - (dot3(goal_vec, rov) / (dist_goal * norm3(rov)));
+  double w2 = 1 - m.div_(dot3(goal_vec, rov), dist_goal * m.sqrt_(dot3(rov, rov)));
   w2 = w2 * w2;
   return w1 * w2;
 }
 
 // updatePositionAndVelocity :253-268
-PMAF_HD void integrate_step(v3 force, double dt, const AgentConsts &c, v3 &p, v3 &v) {
+template <class M>
+PMAF_HD void integrate_step(M &m, v3 force, double dt, const AgentConsts &c, v3 &p, v3 &v) {
   v3 acc = c.unit_mass ? force : div3(force, c.mass);
   const double zacc = dot3(acc, acc);
-  if (norm_gt(zacc, make_thr(13.0))) acc = mul3(acc, 13.0 / sqrt(zacc));
+  if (norm_gt(zacc, make_thr(13.0))) acc = mul3(acc, 13.0 / sqrt(zacc));  // rare: exact built-ins
   const v3 np = mk3((p.x + 0.5 * acc.x * dt * dt) + v.x * dt, (p.y + 0.5 * acc.y * dt * dt) + v.y * dt,
                     (p.z + 0.5 * acc.z * dt * dt) + v.z * dt);
   v = add3(v, mul3(acc, dt));
-  const double vel_norm = norm3(v);
-  if (vel_norm > c.vel_max) v = mul3(v, c.vel_max / vel_norm);
+  const double vel_norm = m.sqrt_(dot3(v, v));
+  const double scale = m.div_(c.vel_max, vel_norm);  // formed unconditionally, used only when clamping
+  if (vel_norm > c.vel_max) v = mul3(v, scale);
   p = np;
+}
+
+// ---- sections of one step: pure functions of registers, evaluated under an arithmetic policy ------
+struct StepNorms {
+  double zg, dist_goal, zv, vn;  // |goal - p|^2, |goal - p|, |v|^2, |v|
+  double seg_len;                // length of the path segment appended by the previous step (:29)
+  v3 vel_des;                    // attractorForce's limited desired velocity (:189-191)
+};
+// Step prologue: four independent square roots (interleaved by the scheduler) and one division.
+// zseg = |p - previous p|^2 (pass has_seg = false on the first step of a rollout).
+template <class M>
+PMAF_HD StepNorms step_norms(M &m, v3 goal_vec, v3 v, double zseg, bool has_seg, const AgentConsts &c) {
+  StepNorms s;
+  s.zg = dot3(goal_vec, goal_vec), s.zv = dot3(v, v);
+  s.dist_goal = m.sqrt_(s.zg), s.vn = m.sqrt_(s.zv);
+  const double seg = m.sqrt_(has_seg ? zseg : 1.0);
+  s.seg_len = has_seg ? seg : 0.0;
+  s.vel_des = desired_velocity(m, goal_vec, c);
+  return s;
+}
+// goal_vec.normalized() (:79) and, for static scenes, rel_vel / vel_norm (:99) — one reciprocal each
+template <bool STATIC_VEL, class M>
+PMAF_HD void step_units(M &m, v3 goal_vec, v3 v, const StepNorms &s, v3 &ghat, v3 &nv_static) {
+  ghat = normalized_zn_m(m, goal_vec, s.zg, s.dist_goal);
+  nv_static = mk3(0.0, 0.0, 0.0);
+  if (STATIC_VEL) {
+    const v3 q = m.div3_(v, s.vn);
+    if (s.vn != 0) nv_static = q;
+  }
+}
+// everything after the circular force and its attractor scaling: repulsion, attraction, integration
+template <class M>
+PMAF_HD void finish_step(M &m, v3 &force, double k_goal_scale, const StepNorms &s, v3 o_sentinel, double dt,
+                         const AgentConsts &c, v3 &p, v3 &v) {
+  force = add_repel_force(force, p, o_sentinel, c);
+  force = add_attractor_force(force, s.vel_des, v, k_goal_scale, c);
+  integrate_step(m, force, dt, c, p, v);
 }
 
 // CfAgent::setVelocity :54-61

@@ -8,10 +8,13 @@ namespace pmaf {
 // Shared memory of a rollout CTA:
 //   [0, 16)                      mbarrier
 //   [16, 16 + img.bytes)         obstacle image (TMA bulk copy of PlannerDev::image)
-//   then per group: uint16 cand[cand_stride], uint32 known[known_words]
+//   then per group: double fbuf[3 * LPA] (ordered force sum staging), uint16 cand[cand_stride],
+//   uint32 known[known_words]
 __host__ __device__ inline uint32_t rollout_cand_stride(int n_obs) { return (uint32_t)((n_obs + 7) & ~7); }
-__host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, int groups, int known_words) {
+__host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, int groups, int lanes_per_agent,
+                                                     int known_words) {
   size_t b = 16 + img.bytes;
+  b += (size_t)groups * 3 * lanes_per_agent * sizeof(double);
   b += (size_t)groups * rollout_cand_stride(img.n_obs) * sizeof(uint16_t);
   b += (size_t)groups * known_words * sizeof(uint32_t);
   return (b + 15) & ~(size_t)15;
@@ -22,17 +25,15 @@ __host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, i
 #pragma nv_exec_check_disable
 template <bool STATIC_VEL, class G>
 PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
-                         const KnownBits &known, int type, const AgentConsts &c, v3 init_pos, double *rot_row,
-                         const double *random_row, v3 goal_vec, double zg, double dist_goal, v3 &p, v3 &v,
+                         double *fbuf, const KnownBits &known, int type, const AgentConsts &c, v3 init_pos,
+                         double *rot_row, const double *random_row, v3 goal_vec, const StepNorms &sn, v3 &p, v3 &v,
                          double &min_obs) {
   constexpr int LPA = G::kLanes;
   const v3 goal = ld3(P.goal);
   const int n_field = P.n_obs - 1;  // the sentinel is excluded from the field loops (:75)
   v3 force = mk3(0.0, 0.0, 0.0);    // resetForce()
   double k_goal_scale = 1.0;
-  const double zv = dot3(v, v);
-  const double vn = sqrt(zv);
-  if (field_gate_open(dist_goal, vn, p, init_pos, c)) {
+  if (field_gate_open(sn.dist_goal, sn.vn, p, init_pos, c)) {
     // ---- broad phase: fp32 sphere test, ordered compaction of candidate indices ----
     const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
     const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
@@ -52,23 +53,45 @@ PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &o
     if (n_cand > 0) {
       g.sync();
       // ---- narrow phase ----
-      const v3 ghat = normalized_zn(goal_vec, zg, dist_goal);  // goal_vec.normalized() (:79)
-      double min_d, closest_d;
-      int closest_i;
-      field_pass<STATIC_VEL>(g, obs, n_field, cand, n_cand, type, p, v, zv, vn, goal, ghat, c.shell, c.k_circ, known,
-                             rot_row, random_row, force, min_d, closest_d, closest_i);
-      if (min_d < min_obs) min_obs = min_d;
-      if (norm_gt(dot3(force, force), make_thr(1e-5))) {  // :319-321
-        k_goal_scale =
-            closest_i < 0 ? 1.0 : attractor_scaling(goal_vec, dist_goal, p, v, vn, c, closest_d, obs.pos(closest_i));
+      v3 ghat, nv_static;
+      {
+        FastMath fm;
+        step_units<STATIC_VEL>(fm, goal_vec, v, sn, ghat, nv_static);
+        if (fm.bad()) {
+          ExactMath em;
+          step_units<STATIC_VEL>(em, goal_vec, v, sn, ghat, nv_static);
+        }
       }
+      double min_d, kgs_closest;
+      bool has_closest;
+      field_pass<STATIC_VEL>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat, c, known,
+                             rot_row, random_row, fbuf, force, min_d, has_closest, kgs_closest);
+      if (min_d < min_obs) min_obs = min_d;
+      // `if (force_.norm() > 1e-5) k_goal_scale = attractorForceScaling()` (:319-321); no close obstacle: 1 (:212-214)
+      if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
       g.sync();  // cand[] is rewritten by the next step's broad phase
     }
   }
-  const int s = P.n_obs - 1;
-  force = add_repel_force(force, p, obs.pos(s), obs.rsum(s), c);
-  force = add_attractor_force(force, goal_vec, v, k_goal_scale, c);
-  integrate_step(force, P.pred_dt, c, p, v);
+  const v3 o_s = obs.pos(P.n_obs - 1);
+  const v3 p0 = p, v0 = v, f0 = force;
+  FastMath fm;
+  finish_step(fm, force, k_goal_scale, sn, o_s, P.pred_dt, c, p, v);
+  if (fm.bad()) {
+    ExactMath em;
+    p = p0, v = v0, force = f0;
+    finish_step(em, force, k_goal_scale, sn, o_s, P.pred_dt, c, p, v);
+  }
+}
+
+// step prologue under FastMath with the exact re-evaluation
+PMAF_HDT StepNorms step_norms_checked(v3 goal_vec, v3 v, double zseg, bool has_seg, const AgentConsts &c) {
+  FastMath fm;
+  StepNorms sn = step_norms(fm, goal_vec, v, zseg, has_seg, c);
+  if (fm.bad()) {
+    ExactMath em;
+    sn = step_norms(em, goal_vec, v, zseg, has_seg, c);
+  }
+  return sn;
 }
 
 // Rollout of every agent to termination. Each group continues ITS agent from the agent's current
@@ -81,7 +104,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   unsigned char *img = smem + 16;
   const int groups = blockDim.x / LPA;
-  uint16_t *cand_all = reinterpret_cast<uint16_t *>(img + P.img.bytes);
+  double *fbuf_all = reinterpret_cast<double *>(img + P.img.bytes);
+  uint16_t *cand_all = reinterpret_cast<uint16_t *>(fbuf_all + (size_t)groups * 3 * LPA);
   const uint32_t cand_stride = rollout_cand_stride(P.n_obs);
   uint32_t *known_all = reinterpret_cast<uint32_t *>(cand_all + (size_t)groups * cand_stride);
 
@@ -101,6 +125,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
   const int a = blockIdx.x * groups + group_in_block;  // local agent index
   const bool have_agent = a < P.n_agents;
   uint16_t *cand = cand_all + (size_t)group_in_block * cand_stride;
+  double *fbuf = fbuf_all + (size_t)group_in_block * 3 * LPA;
   KnownBits known;
   known.w = known_all + (size_t)group_in_block * P.known_words;
 
@@ -108,7 +133,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
   v3 p = mk3(0, 0, 0), v = p, init_pos = p;
   double min_obs = 0, path_len = 0, ws_cost = 0;
   int n_path = 0, type = 0;
-  AgentConsts k = make_agent_consts(0, 0, 0, 1, P.shell, P.vel_max, P.approach_dist, P.mass);
+  AgentConsts k = make_agent_consts(0, 0, 0, 1, P.shell, P.vel_max, P.approach_dist, P.mass, 0);
   double *rot_row = nullptr;
   const double *random_row = nullptr;
   if (have_agent) {
@@ -120,9 +145,6 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
     ws_cost = P.ws_cost[a];
     n_path = P.n_path[a];
     type = agent_type_of_index(P.first_agent + a);
-    const int ga = P.first_agent + a;  // gains are indexed by GLOBAL agent index
-    k = make_agent_consts(P.k_attr[ga], P.k_circ[ga], P.k_repel[ga], P.k_damp[ga], P.shell, P.vel_max,
-                          P.approach_dist, P.mass);
     rot_row = P.rot + (size_t)a * P.n_obs * 3;
     random_row = P.random_vecs + (size_t)a * P.n_obs * 3;
     for (int w = g.gl; w < P.known_words; w += LPA) known.w[w] = P.known[(size_t)a * P.known_words + w];
@@ -140,6 +162,11 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
   obs.vz = reinterpret_cast<const double *>(img + P.img.off_vz);
   obs.dynamic = DYNAMIC;
   const float4 *bp = reinterpret_cast<const float4 *>(img + P.img.off_bp);
+  if (have_agent) {
+    const int ga = P.first_agent + a;  // gains are indexed by GLOBAL agent index
+    k = make_agent_consts(P.k_attr[ga], P.k_circ[ga], P.k_repel[ga], P.k_damp[ga], P.shell, P.vel_max,
+                          P.approach_dist, P.mass, obs.rsum(P.n_obs - 1));
+  }
 
   const v3 goal = ld3(P.goal);
   const unsigned long long t0 = global_timer_ns();
@@ -147,16 +174,20 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
   bool alive = have_agent;
   double *path_row = have_agent ? P.paths + (size_t)a * P.max_steps * 3 : nullptr;
 
+  double zseg = 1.0;  // |last path segment|^2: its square root joins the next step's prologue
+  bool has_seg = false;
   for (;;) {
     if (alive) {
       const v3 goal_vec = sub3(goal, p);
-      const double zg = dot3(goal_vec, goal_vec);
-      const double dist_goal = sqrt(zg);
-      if (dist_goal > 0.1 && n_path < P.max_steps) {  // :310-311
+      const StepNorms sn = step_norms_checked(goal_vec, v, zseg, has_seg, k);
+      path_len += sn.seg_len;  // getPathLength term (:29), in path order
+      has_seg = false;
+      if (sn.dist_goal > 0.1 && n_path < P.max_steps) {  // :310-311
         const v3 prev = p;
-        agent_step<!DYNAMIC>(g, P, obs, bp, cand, known, type, k, init_pos, rot_row, random_row, goal_vec, zg,
-                             dist_goal, p, v, min_obs);
-        path_len += norm3(sub3(p, prev));  // getPathLength term (:29)
+        agent_step<!DYNAMIC>(g, P, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, sn, p,
+                             v, min_obs);
+        const v3 seg = sub3(p, prev);
+        zseg = dot3(seg, seg), has_seg = true;
         if (P.fused_valid) ws_cost = add_workspace_cost(ws_cost, p, P.fused_cost.ws, P.fused_cost.k_workspace);
         if (g.gl == 0) st3(path_row + (size_t)n_path * 3, p);
         ++n_path;
@@ -461,6 +492,7 @@ struct RealArgs {
 
 // one warp
 __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, const RealArgs R) {
+  __shared__ double fbuf[3 * 32];
   const Group<32> g;
   LiveObstacles obs;
   obs.p = R.obs_pos, obs.v = R.obs_vel, obs.r = R.obs_rad, obs.agent_rad = P.rad;
@@ -469,7 +501,7 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   int aid = R.agent_id;
   if (aid < 0) aid = R.eval->best_index;
   const AgentConsts k = make_agent_consts(P.k_attr[aid], P.k_circ[aid], P.k_repel[aid], P.k_damp[aid], P.shell,
-                                          P.vel_max, P.approach_dist, P.mass);
+                                          P.vel_max, P.approach_dist, P.mass, obs.rsum(R.n_obs - 1));
   const int type = R.best->type;
   const v3 goal = ld3(R.goal);
   const v3 init_pos = ld3(R.real->init_pos);
@@ -478,27 +510,21 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   const int n_field = R.n_obs - 1;
   for (int s = 0; s < R.steps; ++s) {
     force = mk3(0.0, 0.0, 0.0);
-    double k_goal_scale = 1.0;
     const v3 goal_vec = sub3(goal, p);
-    const double zg = dot3(goal_vec, goal_vec);
-    const double dist_goal = sqrt(zg);
-    const double zv = dot3(v, v);
-    const double vn = sqrt(zv);
-    if (field_gate_open(dist_goal, vn, p, init_pos, k)) {
-      double min_d, closest_d;
-      int closest_i;
-      const v3 ghat = normalized_zn(goal_vec, zg, dist_goal);
-      field_pass<false>(g, obs, n_field, nullptr, n_field, type, p, v, zv, vn, goal, ghat, P.shell, k.k_circ, known,
-                        R.rot, R.best_random, force, min_d, closest_d, closest_i);
-      if (norm_gt(dot3(force, force), make_thr(1e-5))) {
-        k_goal_scale =
-            closest_i < 0 ? 1.0 : attractor_scaling(goal_vec, dist_goal, p, v, vn, k, closest_d, obs.pos(closest_i));
-      }
+    ExactMath em;  // scalar parts of the single real-agent step: built-in arithmetic
+    const StepNorms sn = step_norms(em, goal_vec, v, 1.0, false, k);
+    double k_goal_scale = 1.0;
+    if (field_gate_open(sn.dist_goal, sn.vn, p, init_pos, k)) {
+      double min_d, kgs_closest;
+      bool has_closest;
+      v3 ghat, nv_unused;
+      step_units<false>(em, goal_vec, v, sn, ghat, nv_unused);
+      field_pass<false>(g, obs, n_field, nullptr, n_field, type, p, v, goal_vec, sn, nv_unused, goal, ghat, k, known,
+                        R.rot, R.best_random, fbuf, force, min_d, has_closest, kgs_closest);
+      if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
       g.sync();
     }
-    force = add_repel_force(force, p, obs.pos(R.n_obs - 1), obs.rsum(R.n_obs - 1), k);
-    force = add_attractor_force(force, goal_vec, v, k_goal_scale, k);
-    integrate_step(force, R.delta_t, k, p, v);
+    finish_step(em, force, k_goal_scale, sn, obs.pos(R.n_obs - 1), R.delta_t, k, p, v);
     if (g.gl == 0) st3(R.path_out + 3 * s, p);
   }
   if (g.gl == 0 && R.steps > 0) {

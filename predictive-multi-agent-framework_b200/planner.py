@@ -49,7 +49,7 @@ API_SYMBOLS = [
     "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
     "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters",
     "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
-    "pmaf_flush_l2", "pmaf_measure_fp64_peak",
+    "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math",
 ]
 
 
@@ -121,6 +121,7 @@ def load_library():
     lib.pmaf_timer_stop.argtypes = [H, _dp]
     lib.pmaf_flush_l2.argtypes = [H]
     lib.pmaf_measure_fp64_peak.argtypes = [H, _dp]
+    lib.pmaf_selftest_math.argtypes = [H, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -354,3 +355,8 @@ class CfManager:
         t = C.c_double()
         self._check(self.lib.pmaf_measure_fp64_peak(self.h, C.byref(t)))
         return t.value
+
+    def selftest_math(self, samples, seed=1):
+        out = (C.c_uint64 * 5)()
+        self._check(self.lib.pmaf_selftest_math(self.h, int(samples), int(seed), out))
+        return dict(zip(("sqrt_mismatch", "div_mismatch", "div3_mismatch", "flagged", "compared"), list(out)))

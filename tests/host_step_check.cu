@@ -36,30 +36,34 @@ extern "C" int hoststep_rollout(int n_obs, const double *obs_pos, const double *
   obs.px = px.data(), obs.py = py.data(), obs.pz = pz.data(), obs.rs = rs.data();
   obs.vx = vx.data(), obs.vy = vy.data(), obs.vz = vz.data(), obs.dynamic = dynamic;
   std::vector<uint16_t> cand(n_obs + 8);
+  double fbuf[3];
   std::vector<uint32_t> words((n_obs + 31) / 32, 0u);
   for (int i = 0; i < n_obs; ++i)
     if (known_io[i]) words[i >> 5] |= 1u << (i & 31);
   KnownBits known;
   known.w = words.data();
   HostGroup g;
-  const AgentConsts k = make_agent_consts(k_attr, k_circ, k_repel, k_damp, shell, vmax, approach, mass);
+  const AgentConsts k = make_agent_consts(k_attr, k_circ, k_repel, k_damp, shell, vmax, approach, mass, rs[n_obs - 1]);
   v3 p = ld3(p0), v = ld3(v0);
   const v3 gl = ld3(goal), ip = ld3(init_pos);
   double min_obs = min_obs0, path_len = 0.0;
   int n_path = *n_path_io;
+  double zseg = 1.0;
+  bool has_seg = false;
   for (;;) {
     const v3 goal_vec = sub3(gl, p);
-    const double zg = dot3(goal_vec, goal_vec);
-    const double dist_goal = sqrt(zg);
-    if (!(dist_goal > 0.1 && n_path < H)) break;
+    const StepNorms sn = step_norms_checked(goal_vec, v, zseg, has_seg, k);
+    path_len += sn.seg_len;
+    has_seg = false;
+    if (!(sn.dist_goal > 0.1 && n_path < H)) break;
     const v3 prev = p;
     if (dynamic)
-      agent_step<false>(g, P, obs, bp.data(), cand.data(), known, type, k, ip, rot_io, random_vecs, goal_vec, zg,
-                        dist_goal, p, v, min_obs);
+      agent_step<false>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
+                        min_obs);
     else
-      agent_step<true>(g, P, obs, bp.data(), cand.data(), known, type, k, ip, rot_io, random_vecs, goal_vec, zg,
-                       dist_goal, p, v, min_obs);
-    path_len += norm3(sub3(p, prev));
+      agent_step<true>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
+                       min_obs);
+    { const v3 seg = sub3(p, prev); zseg = dot3(seg, seg); has_seg = true; }
     st3(path + 3 * n_path, p);
     ++n_path;
     if (dynamic) {
