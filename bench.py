@@ -157,11 +157,12 @@ def run_ours(args, rank, world, local_rank):
     # weak scaling: every GPU owns `agents` agents of a population of agents * world
     sc = sc1 if world == 1 else sc1.with_(num_agents=sc1.num_agents * world, name=f"{sc1.name}_x{world}")
     if world == 1:
-        mgr = planner.CfManager(local_rank, lanes_per_agent=args.lanes, block_threads=args.block)
+        mgr = planner.CfManager(local_rank, lanes_per_agent=args.lanes, block_threads=args.block, occupancy=args.occ)
     else:
         from pmaf_b200 import sharded
 
-        mgr = sharded.ShardedCfManager(local_rank, rank, world, lanes_per_agent=args.lanes, block_threads=args.block)
+        mgr = sharded.ShardedCfManager(local_rank, rank, world, lanes_per_agent=args.lanes, block_threads=args.block,
+                                       occupancy=args.occ)
     feed = loop.ObstacleFeed(sc)
     loop.plan_begin(mgr, sc)
 
@@ -235,7 +236,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(sc, world, {"lanes_per_agent": c1["lanes_per_agent"],
                                                   "block_threads": c1["block_threads"], "grid": c1["grid_blocks"],
-                                                  "smem_bytes": c1["smem_bytes"]}),
+                                                  "smem_bytes": c1["smem_bytes"], "occupancy_build": c1["occupancy_build"]}),
             "clocks": clocks,
             "e2e": {"value": e2e_steps_all / e2e_s, "unit": "agent-steps/s",
                     "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) / args.steps,
@@ -277,6 +278,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--occ", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -204,10 +204,13 @@ typedef struct {
   int block_threads;
   int grid_blocks;
   int smem_bytes;
+  int occupancy_build;
 } pmaf_counters;
 int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out);
-/* rollout kernel shape override for experiments: lanes_per_agent in {0 (auto), 4, 8, 16, 32} */
-int pmaf_set_tuning(pmaf_planner *p, int lanes_per_agent, int block_threads);
+/* rollout kernel shape override for experiments: lanes_per_agent in {0 (auto), 4, 8, 16, 32};
+ * block_threads 0 (auto) or a multiple of 32 up to 256; occupancy 0 (auto), 1, 3 or 4 = resident CTAs
+ * per SM the kernel's register budget is compiled for (255 / 170 / 128 registers per thread). */
+int pmaf_set_tuning(pmaf_planner *p, int lanes_per_agent, int block_threads, int occupancy);
 /* By default an obstacle list that is byte-identical to the last one uploaded is not copied to the
  * device again (static scenes); dedup = 0 forces the host->device copy on every call. */
 int pmaf_set_upload_dedup(pmaf_planner *p, int dedup);
@@ -225,6 +228,9 @@ int pmaf_measure_fp64_peak(pmaf_planner *p, double *tflops);
  * mismatches, shared-reciprocal vector division mismatches, operands rejected by the range check,
  * comparisons made }. Any mismatch is a bug. */
 int pmaf_selftest_math(pmaf_planner *p, uint64_t samples, uint64_t seed, uint64_t out[5]);
+/* Developer instrumentation: cycles spent per section of the step loop by the first 64 agents in
+ * their last rollout, out[64][12]; all zero unless libpmaf was built with -DPMAF_SECTION_TIMERS. */
+int pmaf_get_section_cycles(pmaf_planner *p, long long *out);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,7 @@ struct pmaf_planner {
   bool nccl_owned = false;
   DevBuf<unsigned long long> step_counter;
   DevBuf<unsigned char> l2_scratch;
+  DevBuf<long long> section_cycles;
   // host mirrors
   std::vector<double> h_obs_pos, h_obs_vel, h_obs_rad;  // agents' copy
   std::vector<double> h_live;                            // last uploaded live list (pos|vel|rad)
@@ -137,7 +138,7 @@ struct pmaf_planner {
   bool seeded = false;
   uint64_t seed = 0;
   // tuning + counters
-  int tune_lpa = 0, tune_block = 0;
+  int tune_lpa = 0, tune_block = 0, tune_occ = 0;
   pmaf_counters ctr{};
 };
 
@@ -168,6 +169,7 @@ static PlannerDev make_dev(const pmaf_planner *p) {
   d.image = p->image.p, d.img = p->img;
   d.fused_cost = p->last_cost, d.fused_valid = p->fused_valid ? 1 : 0;
   d.step_counter = p->step_counter.p;
+  d.section_cycles = p->section_cycles.p;
   return d;
 }
 
@@ -359,6 +361,10 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(p->real.resize(1));
   CU(p->step_counter.resize(2));
   CU(p->scratch.resize(16));
+#if defined(PMAF_SECTION_TIMERS)
+  CU(p->section_cycles.resize(64 * 12));
+  CU(cudaMemsetAsync(p->section_cycles.p, 0, 64 * 12 * sizeof(long long), p->stream));
+#endif
   CU(cudaMemsetAsync(p->best.p, 0, sizeof(DeviceBest), p->stream));
   CU(cudaMemsetAsync(p->real.p, 0, sizeof(RealState), p->stream));
   CU(cudaMemsetAsync(p->step_counter.p, 0, 2 * sizeof(unsigned long long), p->stream));
@@ -378,6 +384,7 @@ extern "C" int pmaf_destroy(pmaf_planner *p) {
         &p->scratch, &p->real_path_out})
     b->release();
   p->l2_scratch.release();
+  p->section_cycles.release();
   p->n_path.release(), p->reached.release(), p->known.release(), p->image.release(), p->real_known.release();
   p->real.release(), p->best.release(), p->eval.release(), p->rec.release(), p->step_counter.release();
   p->rec_all.release();
@@ -683,7 +690,16 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
   const size_t smem = rollout_smem_bytes(p->img, groups, LPA, p->known_words);
   REQUIRE(smem <= 227 * 1024, PMAF_ERR_ARG, "rollout needs %zu B of shared memory (> 227 KB): too many obstacles",
           smem);
-  auto kern = dynamic ? rollout_kernel<LPA, true> : rollout_kernel<LPA, false>;
+  // many warps per SM: the 128-register build keeps 16 warps resident; few: the 255-register build
+  int occ = p->tune_occ;
+  if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 4 * 148) ? 3 : 1;
+  if (LPA != 32 || block > 128) occ = 1;  // the occupancy builds exist for warp-per-agent CTAs of <= 128 threads
+  auto kern = dynamic ? rollout_kernel<LPA, true, 1> : rollout_kernel<LPA, false, 1>;
+  if constexpr (LPA == 32) {
+    if (occ == 3) kern = dynamic ? rollout_kernel<LPA, true, 3> : rollout_kernel<LPA, false, 3>;
+    if (occ == 4) kern = dynamic ? rollout_kernel<LPA, true, 4> : rollout_kernel<LPA, false, 4>;
+  }
+  p->ctr.occupancy_build = occ;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p->ctr.lanes_per_agent = LPA, p->ctr.block_threads = block, p->ctr.grid_blocks = grid, p->ctr.smem_bytes = (int)smem;
   return launch(p, kern, dim3(grid), dim3(block), smem, d);
@@ -695,9 +711,10 @@ static void pick_rollout_shape(const pmaf_planner *p, int &lpa, int &block) {
     block = p->tune_block;
   } else {
     // small populations are latency-bound: one warp per CTA spreads them over all 148 SMs;
-    // large ones pack 4 warps per CTA to amortise the obstacle staging
+    // large ones pack 2 warps per CTA (measured best on 4096 agents x 256 obstacles) and use the
+    // 170-register build so that 6+ warps stay resident per SM
     const long long warps = ((long long)p->A * lpa + 31) / 32;
-    block = warps <= 2 * 148 ? 32 : 128;
+    block = warps <= 2 * 148 ? 32 : 64;
   }
   if (block < lpa) block = lpa;
 }
@@ -1110,14 +1127,16 @@ extern "C" int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out) {
   return 0;
 }
 
-extern "C" int pmaf_set_tuning(pmaf_planner *p, int lanes_per_agent, int block_threads) {
+extern "C" int pmaf_set_tuning(pmaf_planner *p, int lanes_per_agent, int block_threads, int occupancy) {
   ENTER(p);
   REQUIRE(lanes_per_agent == 0 || lanes_per_agent == 4 || lanes_per_agent == 8 || lanes_per_agent == 16 ||
               lanes_per_agent == 32,
           PMAF_ERR_ARG, "pmaf_set_tuning: lanes_per_agent must be 0, 4, 8, 16 or 32");
   REQUIRE(block_threads == 0 || (block_threads >= 32 && block_threads <= 256 && block_threads % 32 == 0),
           PMAF_ERR_ARG, "pmaf_set_tuning: block_threads must be 0 or a multiple of 32 in [32, 256]");
-  p->tune_lpa = lanes_per_agent, p->tune_block = block_threads;
+  REQUIRE(occupancy == 0 || occupancy == 1 || occupancy == 3 || occupancy == 4, PMAF_ERR_ARG,
+          "pmaf_set_tuning: occupancy must be 0 (auto), 1, 3 or 4");
+  p->tune_lpa = lanes_per_agent, p->tune_block = block_threads, p->tune_occ = occupancy;
   return 0;
 }
 
@@ -1289,5 +1308,20 @@ extern "C" int pmaf_selftest_math(pmaf_planner *p, uint64_t samples, uint64_t se
   CU(cudaStreamSynchronize(p->stream));
   for (int i = 0; i < 5; ++i) out[i] = h[i];
   d.release();
+  return 0;
+}
+
+// Per-section cycle counters of the first 64 agents' last rollout (all zero unless the library was
+// built with -DPMAF_SECTION_TIMERS); out[64][12].
+extern "C" int pmaf_get_section_cycles(pmaf_planner *p, long long *out) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  if (!p->section_cycles.p) {
+    memset(out, 0, 64 * 12 * sizeof(long long));
+    return 0;
+  }
+  if (int rc = finish_rollout(p)) return rc;
+  CU(cudaMemcpyAsync(out, p->section_cycles.p, 64 * 12 * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
   return 0;
 }

@@ -41,6 +41,24 @@ constexpr int kMaxObstacles = 4096;  // candidate indices are uint16; the smem i
 #endif
 #define PMAF_HDT __host__ __device__ __forceinline__
 
+// Optional per-section cycle counters (build with -DPMAF_SECTION_TIMERS: tools/section_timers.py).
+#if defined(PMAF_SECTION_TIMERS) && defined(__CUDA_ARCH__)
+#define PMAF_T(k)                                            \
+  do {                                                       \
+    const long long t_now_ = clock64();                      \
+    pmaf_sec_[k] += t_now_ - pmaf_t_;                        \
+    pmaf_t_ = t_now_;                                        \
+  } while (0)
+#define PMAF_T_DECL long long pmaf_sec_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pmaf_t_ = clock64()
+#define PMAF_T_ARGS , long long *pmaf_sec_, long long &pmaf_t_
+#define PMAF_T_PASS , pmaf_sec_, pmaf_t_
+#else
+#define PMAF_T(k) do { } while (0)
+#define PMAF_T_DECL do { } while (0)
+#define PMAF_T_ARGS
+#define PMAF_T_PASS
+#endif
+
 // Cost parameters of CfManager::evaluateAgents (cf_manager.cpp:293-297)
 struct CostParams {
   double k_goal_dist, k_path_len, k_safe_dist, k_workspace;
@@ -113,6 +131,7 @@ struct PlannerDev {  // kernel argument, passed by value
   int fused_valid;
   // outputs
   unsigned long long *step_counter;  // [0] executed integration steps of this rollout, [1] running total
+  long long *section_cycles;         // [64][12] per-section cycle counters (PMAF_SECTION_TIMERS builds)
 };
 
 // ---- small PTX wrappers (TMA bulk copy + mbarrier) ---------------------------------------------------
@@ -393,7 +412,7 @@ template <bool STATIC_VEL, class G, class Obs, class Known>
 PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t *cand, int n_cand, int type, v3 p,
                          v3 v, v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat,
                          const AgentConsts &c, const Known &known, double *rot_row, const double *random_row,
-                         double *fbuf, v3 &force, double &min_d, bool &has_closest, double &kgs_closest) {
+                         double *fbuf, v3 &force, double &min_d, bool &has_closest, double &kgs_closest PMAF_T_ARGS) {
   constexpr int LPA = G::kLanes;
   force = mk3(0.0, 0.0, 0.0);
   double lmin = (double)INFINITY;
@@ -411,6 +430,7 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     if (g.ballot(fm.bad()))
       r = eval_candidate_exact<STATIC_VEL>(g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat,
                                            c, known, rot_row, random_row);
+    PMAF_T(3);
     // ---- commit ----
     if (r.d < lcd) lcd = r.d, lci = i, lkgs = r.kgs;  // the search ignores the skip test (:201-211)
     if (r.counts_min && r.d < lmin) lmin = r.d;
@@ -434,6 +454,7 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
       }
       g.sync();
     }
+    PMAF_T(4);
   }
   // reductions only when they can matter
   const bool shell_ok = c.shell > 0.0;  // non-negative keys for the integer-ordered reductions
@@ -449,6 +470,7 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     const unsigned who = g.ballot(mine == lci);
     kgs_closest = g.bcast(lkgs, PMAF_FFS(who) - 1);
   }
+  PMAF_T(5);
 }
 
 }  // namespace pmaf

@@ -77,6 +77,24 @@ PMAF_HD v3 normalized3(v3 a) {
 // std::max(d, 1e-5) (cf_agent.cpp:85): NaN stays NaN
 PMAF_HD double clamp_dist(double d) { return d < 1e-5 ? 1e-5 : d; }
 
+// ---- pinning loop invariants in registers ------------------------------------------------------------
+// Kernel parameters live in the constant bank; ptxas re-reads them (LDCU/LDC) at every use inside the
+// step loop, and a dependent use waits the full constant-load latency (measured: six
+// load->compare pairs of the workspace cost took ~600 cycles per step). Passing a value through an
+// opaque asm makes it an ordinary register value for the rest of the kernel.
+PMAF_HD double keep(double x) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+d"(x));
+#endif
+  return x;
+}
+PMAF_HD int keep(int x) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(x));
+#endif
+  return x;
+}
+
 // ---- arithmetic policies ---------------------------------------------------------------------------
 // The reference's x86-64 build rounds every sqrt and division correctly (IEEE). Two ways to get the
 // same bits on the GPU:
@@ -275,6 +293,11 @@ PMAF_HD AgentConsts make_agent_consts(double k_attr, double k_circ, double k_rep
   const double far = (shell + rsum_s) + 1e-9;  // absolute margin >> rounding of n and n - rsum
   c.repel_far2 = far * far * (1.0 + 1e-15);
   c.unit_mass = mass == 1.0;
+  c.k_attr = keep(c.k_attr), c.k_circ = keep(c.k_circ), c.k_repel = keep(c.k_repel), c.k_damp = keep(c.k_damp);
+  c.attr_ratio = keep(c.attr_ratio), c.inv_shell = keep(c.inv_shell), c.half_vmax = keep(c.half_vmax);
+  c.vmax90 = keep(c.vmax90), c.shell = keep(c.shell), c.vel_max = keep(c.vel_max);
+  c.approach_dist = keep(c.approach_dist), c.mass = keep(c.mass), c.rsum_s = keep(c.rsum_s);
+  c.repel_far2 = keep(c.repel_far2);
   return c;
 }
 
@@ -472,6 +495,15 @@ PMAF_HD v3 clamp_velocity(v3 v, double vel_max) {
 
 // workspace term of one path point, CfManager::evaluateAgents cf_manager.cpp:302-323
 // ws = [x+, x-, y+, y-, z+, z-]
+struct WsParams {
+  double ws[6], k_workspace;
+};
+PMAF_HD WsParams pin_ws(const double *ws, double k_workspace) {
+  WsParams w;
+  for (int i = 0; i < 6; ++i) w.ws[i] = keep(ws[i]);
+  w.k_workspace = keep(k_workspace);
+  return w;
+}
 PMAF_HD double add_workspace_cost(double cost, v3 q, const double *ws, double k_workspace) {
   double t;
   if (q.x > ws[0]) {

@@ -20,20 +20,28 @@ __host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, i
   return (b + 15) & ~(size_t)15;
 }
 
+// loop-invariant planner values, pinned in registers (see keep())
+struct StepEnv {
+  v3 goal;
+  int n_obs;
+  double pred_dt;
+};
+
 // One integration step of one agent (loop body of cfPrediction, cf_agent.cpp:312-326).
 // Returns the new position in p / velocity in v; updates min_obs.
 #pragma nv_exec_check_disable
 template <bool STATIC_VEL, class G>
-PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
+PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
                          double *fbuf, const KnownBits &known, int type, const AgentConsts &c, v3 init_pos,
                          double *rot_row, const double *random_row, v3 goal_vec, const StepNorms &sn, v3 &p, v3 &v,
-                         double &min_obs) {
+                         double &min_obs PMAF_T_ARGS) {
   constexpr int LPA = G::kLanes;
-  const v3 goal = ld3(P.goal);
+  const v3 goal = P.goal;
   const int n_field = P.n_obs - 1;  // the sentinel is excluded from the field loops (:75)
   v3 force = mk3(0.0, 0.0, 0.0);    // resetForce()
   double k_goal_scale = 1.0;
   if (field_gate_open(sn.dist_goal, sn.vn, p, init_pos, c)) {
+    PMAF_T(8);
     // ---- broad phase: fp32 sphere test, ordered compaction of candidate indices ----
     const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
     const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
@@ -50,6 +58,7 @@ PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &o
       if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
       n_cand += PMAF_POPC(m);
     }
+    PMAF_T(1);
     if (n_cand > 0) {
       g.sync();
       // ---- narrow phase ----
@@ -62,10 +71,11 @@ PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &o
           step_units<STATIC_VEL>(em, goal_vec, v, sn, ghat, nv_static);
         }
       }
+      PMAF_T(2);
       double min_d, kgs_closest;
       bool has_closest;
       field_pass<STATIC_VEL>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat, c, known,
-                             rot_row, random_row, fbuf, force, min_d, has_closest, kgs_closest);
+                             rot_row, random_row, fbuf, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
       if (min_d < min_obs) min_obs = min_d;
       // `if (force_.norm() > 1e-5) k_goal_scale = attractorForceScaling()` (:319-321); no close obstacle: 1 (:212-214)
       if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
@@ -81,6 +91,7 @@ PMAF_HDT void agent_step(const G &g, const PlannerDev &P, const SmemObstacles &o
     p = p0, v = v0, force = f0;
     finish_step(em, force, k_goal_scale, sn, o_s, P.pred_dt, c, p, v);
   }
+  PMAF_T(6);
 }
 
 // step prologue under FastMath with the exact re-evaluation
@@ -98,8 +109,11 @@ PMAF_HDT StepNorms step_norms_checked(v3 goal_vec, v3 v, double zseg, bool has_s
 // state (latest path point, velocity, min_obs_dist, known flags, path length, workspace cost) —
 // which resetEEAgents made uniform in the normal tick order — so any call order of the reference
 // API keeps its meaning; an already terminated agent executes zero steps.
-template <int LPA, bool DYNAMIC>
-__global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
+// OCC = resident CTAs per SM the register budget is sized for: 1 (up to 255 registers: the latency-bound
+// case, one warp per scheduler), or 3 / 4 CTAs of 128 threads (170 / 128 registers: populations that
+// fill the machine trade registers for resident warps).
+template <int LPA, bool DYNAMIC, int OCC>
+__global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(const PlannerDev P) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
   unsigned char *img = smem + 16;
@@ -168,7 +182,13 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
                           P.approach_dist, P.mass, obs.rsum(P.n_obs - 1));
   }
 
-  const v3 goal = ld3(P.goal);
+  StepEnv env;
+  env.goal = mk3(keep(P.goal[0]), keep(P.goal[1]), keep(P.goal[2]));
+  env.n_obs = keep(P.n_obs), env.pred_dt = keep(P.pred_dt);
+  const v3 goal = env.goal;
+  const int max_steps = keep(P.max_steps);
+  const bool fused = keep(P.fused_valid) != 0;
+  const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace);
   const unsigned long long t0 = global_timer_ns();
   int steps_run = 0;
   bool alive = have_agent;
@@ -176,22 +196,26 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
 
   double zseg = 1.0;  // |last path segment|^2: its square root joins the next step's prologue
   bool has_seg = false;
+  PMAF_T_DECL;
   for (;;) {
     if (alive) {
       const v3 goal_vec = sub3(goal, p);
       const StepNorms sn = step_norms_checked(goal_vec, v, zseg, has_seg, k);
+      PMAF_T(0);
       path_len += sn.seg_len;  // getPathLength term (:29), in path order
       has_seg = false;
-      if (sn.dist_goal > 0.1 && n_path < P.max_steps) {  // :310-311
+      if (sn.dist_goal > 0.1 && n_path < max_steps) {  // :310-311
         const v3 prev = p;
-        agent_step<!DYNAMIC>(g, P, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, sn, p,
-                             v, min_obs);
+        agent_step<!DYNAMIC>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, sn, p,
+                             v, min_obs PMAF_T_PASS);
         const v3 seg = sub3(p, prev);
         zseg = dot3(seg, seg), has_seg = true;
-        if (P.fused_valid) ws_cost = add_workspace_cost(ws_cost, p, P.fused_cost.ws, P.fused_cost.k_workspace);
+        if (fused) ws_cost = add_workspace_cost(ws_cost, p, wsp.ws, wsp.k_workspace);
+        PMAF_T(9);
         if (g.gl == 0) st3(path_row + (size_t)n_path * 3, p);
         ++n_path;
         ++steps_run;
+        PMAF_T(7);
       } else {
         alive = false;
       }
@@ -206,7 +230,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
       const double *dy = reinterpret_cast<const double *>(img + P.img.off_dy);
       const double *dz = reinterpret_cast<const double *>(img + P.img.off_dz);
       float4 *bpw = const_cast<float4 *>(bp);
-      for (int i = threadIdx.x; i < P.n_obs; i += blockDim.x) {
+      for (int i = threadIdx.x; i < env.n_obs; i += blockDim.x) {
         const double x = px[i] + dx[i], y = py[i] + dy[i], z = pz[i] + dz[i];
         px[i] = x, py[i] = y, pz[i] = z;
         float4 b = bpw[i];
@@ -228,6 +252,10 @@ __global__ void __launch_bounds__(256) rollout_kernel(const PlannerDev P) {
       P.path_len[a] = path_len;
       P.ws_cost[a] = ws_cost;
       P.n_path[a] = n_path;
+#if defined(PMAF_SECTION_TIMERS) && defined(__CUDA_ARCH__)
+      if (a < 64 && P.section_cycles)
+        for (int q = 0; q < 12; ++q) P.section_cycles[a * 12 + q] = pmaf_sec_[q];
+#endif
       if (steps_run > 0) {  // `if (running_)`, :330-337
         P.pred_time_ns[a] = (double)(global_timer_ns() - t0);
         P.reached[a] = norm3(sub3(goal, p)) < 0.100001 ? 1 : 0;
@@ -508,6 +536,7 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   v3 p = ld3(R.real->pos), v = ld3(R.real->vel);
   v3 force = mk3(0.0, 0.0, 0.0);
   const int n_field = R.n_obs - 1;
+  PMAF_T_DECL;
   for (int s = 0; s < R.steps; ++s) {
     force = mk3(0.0, 0.0, 0.0);
     const v3 goal_vec = sub3(goal, p);
@@ -520,7 +549,7 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
       v3 ghat, nv_unused;
       step_units<false>(em, goal_vec, v, sn, ghat, nv_unused);
       field_pass<false>(g, obs, n_field, nullptr, n_field, type, p, v, goal_vec, sn, nv_unused, goal, ghat, k, known,
-                        R.rot, R.best_random, fbuf, force, min_d, has_closest, kgs_closest);
+                        R.rot, R.best_random, fbuf, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
       if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
       g.sync();
     }

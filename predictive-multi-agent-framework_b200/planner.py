@@ -34,7 +34,7 @@ class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("collectives", C.c_uint64), ("rollouts", C.c_uint64), ("agent_steps", C.c_uint64), ("agent_steps_total", C.c_uint64),
                 ("last_rollout_ms", C.c_double), ("rollout_ms_total", C.c_double), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("lanes_per_agent", C.c_int), ("block_threads", C.c_int),
-                ("grid_blocks", C.c_int), ("smem_bytes", C.c_int)]
+                ("grid_blocks", C.c_int), ("smem_bytes", C.c_int), ("occupancy_build", C.c_int)]
 
 
 # every symbol include/pmaf.h declares (tests check that the library exports all of them)
@@ -49,7 +49,7 @@ API_SYMBOLS = [
     "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
     "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters",
     "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
-    "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math",
+    "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles",
 ]
 
 
@@ -115,7 +115,7 @@ def load_library():
     lib.pmaf_get_obstacle_state.argtypes = [H, C.c_int, _ip, _dp]
     lib.pmaf_get_costs.argtypes = [H, _dp]
     lib.pmaf_get_counters.argtypes = [H, C.POINTER(Counters)]
-    lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int]
+    lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int, C.c_int]
     lib.pmaf_set_upload_dedup.argtypes = [H, C.c_int]
     lib.pmaf_timer_start.argtypes = [H]
     lib.pmaf_timer_stop.argtypes = [H, _dp]
@@ -142,12 +142,12 @@ def _i(a):
 class CfManager:
     """ghostplanner::cfplanner::CfManager over the C ABI. One instance = one planner on one GPU."""
 
-    def __init__(self, device=0, lanes_per_agent=0, block_threads=0):
+    def __init__(self, device=0, lanes_per_agent=0, block_threads=0, occupancy=0):
         self.lib = load_library()
         self.h = C.c_void_p()
         self._check(self.lib.pmaf_create(C.byref(self.h), int(device)))
-        if lanes_per_agent or block_threads:
-            self._check(self.lib.pmaf_set_tuning(self.h, int(lanes_per_agent), int(block_threads)))
+        if lanes_per_agent or block_threads or occupancy:
+            self._check(self.lib.pmaf_set_tuning(self.h, int(lanes_per_agent), int(block_threads), int(occupancy)))
         self.A = self.O = self.H = 0
         self.n_global = 0
         self.first_agent = 0
@@ -175,8 +175,8 @@ class CfManager:
     def seed_random_vecs(self, seed):
         self._check(self.lib.pmaf_seed_random_vecs(self.h, int(seed)))
 
-    def set_tuning(self, lanes_per_agent=0, block_threads=0):
-        self._check(self.lib.pmaf_set_tuning(self.h, int(lanes_per_agent), int(block_threads)))
+    def set_tuning(self, lanes_per_agent=0, block_threads=0, occupancy=0):
+        self._check(self.lib.pmaf_set_tuning(self.h, int(lanes_per_agent), int(block_threads), int(occupancy)))
 
     def init(self, goal, delta_t, obs_pos, obs_vel, obs_rad, k_attr, k_circ, k_repel, k_damp, k_manip,
              k_repel_force=(), velocity_max=0.5, approach_dist=0.25, detect_shell_rad=0.8,

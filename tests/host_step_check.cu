@@ -16,10 +16,8 @@ extern "C" int hoststep_rollout(int n_obs, const double *obs_pos, const double *
                                 const double *v0, double min_obs0, unsigned char *known_io, double *rot_io,
                                 const double *random_vecs, float margin, double *path, int *n_path_io,
                                 double *v_out, double *min_obs_out, double *path_len_out) {
-  PlannerDev P{};
-  P.n_agents = 1, P.first_agent = 0, P.n_obs = n_obs, P.max_steps = H;
-  for (int i = 0; i < 3; ++i) P.goal[i] = goal[i];
-  P.shell = shell, P.mass = mass, P.rad = rad, P.vel_max = vmax, P.approach_dist = approach, P.pred_dt = dt;
+  StepEnv P;
+  P.goal = ld3(goal), P.n_obs = n_obs, P.pred_dt = dt;
   bool dynamic = false;
   for (int i = 0; i < 3 * n_obs; ++i) dynamic = dynamic || obs_vel[i] != 0.0;
   std::vector<double> px(n_obs), py(n_obs), pz(n_obs), rs(n_obs), vx(n_obs), vy(n_obs), vz(n_obs), dx(n_obs),
