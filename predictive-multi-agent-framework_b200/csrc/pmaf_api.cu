@@ -110,6 +110,7 @@ struct pmaf_planner {
   DevBuf<unsigned long long> step_counter;
   DevBuf<unsigned char> l2_scratch;
   DevBuf<long long> section_cycles;
+  DevBuf<unsigned> runtime_zero;
   // host mirrors
   std::vector<double> h_obs_pos, h_obs_vel, h_obs_rad;  // agents' copy
   std::vector<double> h_live;                            // last uploaded live list (pos|vel|rad)
@@ -170,6 +171,7 @@ static PlannerDev make_dev(const pmaf_planner *p) {
   d.fused_cost = p->last_cost, d.fused_valid = p->fused_valid ? 1 : 0;
   d.step_counter = p->step_counter.p;
   d.section_cycles = p->section_cycles.p;
+  d.runtime_zero = p->runtime_zero.p;
   return d;
 }
 
@@ -361,6 +363,8 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(p->real.resize(1));
   CU(p->step_counter.resize(2));
   CU(p->scratch.resize(16));
+  CU(p->runtime_zero.resize(1));
+  CU(cudaMemsetAsync(p->runtime_zero.p, 0, sizeof(unsigned), p->stream));
 #if defined(PMAF_SECTION_TIMERS)
   CU(p->section_cycles.resize(64 * 12));
   CU(cudaMemsetAsync(p->section_cycles.p, 0, 64 * 12 * sizeof(long long), p->stream));
@@ -385,6 +389,7 @@ extern "C" int pmaf_destroy(pmaf_planner *p) {
     b->release();
   p->l2_scratch.release();
   p->section_cycles.release();
+  p->runtime_zero.release();
   p->n_path.release(), p->reached.release(), p->known.release(), p->image.release(), p->real_known.release();
   p->real.release(), p->best.release(), p->eval.release(), p->rec.release(), p->step_counter.release();
   p->rec_all.release();

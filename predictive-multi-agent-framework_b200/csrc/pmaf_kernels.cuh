@@ -132,6 +132,7 @@ struct PlannerDev {  // kernel argument, passed by value
   // outputs
   unsigned long long *step_counter;  // [0] executed integration steps of this rollout, [1] running total
   long long *section_cycles;         // [64][12] per-section cycle counters (PMAF_SECTION_TIMERS builds)
+  const unsigned *runtime_zero;      // one word holding 0 (see keep() in pmaf_math.cuh)
 };
 
 // ---- small PTX wrappers (TMA bulk copy + mbarrier) ---------------------------------------------------

@@ -176,19 +176,22 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   obs.vz = reinterpret_cast<const double *>(img + P.img.off_vz);
   obs.dynamic = DYNAMIC;
   const float4 *bp = reinterpret_cast<const float4 *>(img + P.img.off_bp);
+  // always 0, but for the latency build only known at run time (see keep()); the occupancy builds
+  // cannot afford the registers and keep re-reading the constant bank
+  const unsigned rz = OCC == 1 ? *P.runtime_zero : 0u;
   if (have_agent) {
     const int ga = P.first_agent + a;  // gains are indexed by GLOBAL agent index
     k = make_agent_consts(P.k_attr[ga], P.k_circ[ga], P.k_repel[ga], P.k_damp[ga], P.shell, P.vel_max,
-                          P.approach_dist, P.mass, obs.rsum(P.n_obs - 1));
+                          P.approach_dist, P.mass, obs.rsum(P.n_obs - 1), rz);
   }
 
   StepEnv env;
-  env.goal = mk3(keep(P.goal[0]), keep(P.goal[1]), keep(P.goal[2]));
-  env.n_obs = keep(P.n_obs), env.pred_dt = keep(P.pred_dt);
+  env.goal = mk3(keep(P.goal[0], rz), keep(P.goal[1], rz), keep(P.goal[2], rz));
+  env.n_obs = keep(P.n_obs, rz), env.pred_dt = keep(P.pred_dt, rz);
   const v3 goal = env.goal;
-  const int max_steps = keep(P.max_steps);
-  const bool fused = keep(P.fused_valid) != 0;
-  const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace);
+  const int max_steps = keep(P.max_steps, rz);
+  const bool fused = keep(P.fused_valid, rz) != 0;
+  const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace, rz);
   const unsigned long long t0 = global_timer_ns();
   int steps_run = 0;
   bool alive = have_agent;
