@@ -110,7 +110,21 @@ def _with_obstacles(sc, pos, rad, vel=None, **kw):
     return sc.with_(obs_pos=pos, obs_vel=v, obs_rad=rad, **kw)
 
 
-def all_cases():
+def task_cases(golden_dir):
+    """Closed-loop cases on the reference's own task-sequence files (config/tasks/*.yaml), replayed from the
+    inputs stored in tests/golden/task_*.npz (written by make_golden.py where /root/reference exists)."""
+    import glob
+    import os
+
+    out = {}
+    for path in sorted(glob.glob(os.path.join(golden_dir, "task_*.npz"))):
+        d = np.load(path)
+        sc = scenarios.from_arrays(d)
+        out[os.path.basename(path)[:-4]] = closed_loop(sc, int(d["in_ticks"]))
+    return out
+
+
+def all_cases(golden_dir=None):
     S = scenarios
     base = S.small_random(7, num_agents=8, num_obstacles=6, horizon=150)
     axis = base.with_(start=np.array([-0.7, 0.0, 0.65]), goal=np.array([0.5, 0.0, 0.65]))
@@ -153,4 +167,6 @@ def all_cases():
         "position_feedback": feedback(S.small_random(8, num_agents=8, horizon=100), 15),
         "zero_rel_velocity": zero_relative_velocity(S.small_random(9, num_agents=8, num_obstacles=4, horizon=50)),
     }
+    if golden_dir is not None:
+        c.update(task_cases(golden_dir))
     return c

@@ -188,3 +188,32 @@ def from_task_yaml(path, start, goal_index=None, seed=1):
         detect_shell_rad=float(cfg["detect_shell_rad"]),
         prediction_freq_multiple=int(cfg["prediction_freq_multiple"]), frequency_ros=float(cfg["frequency_ros"]),
         velocity=float(cfg["velocity"]), seed=seed, feed_obstacles=feed)
+
+
+_SCALARS = ("name", "num_agents", "k_attr", "k_circ", "k_repel", "k_damp", "k_manip", "k_repel_body", "k_goal_dist",
+            "k_path_len", "k_safe_dist", "k_workspace", "max_prediction_steps", "approach_dist", "detect_shell_rad",
+            "prediction_freq_multiple", "frequency_ros", "velocity", "agent_mass", "radius", "seed", "feed_obstacles",
+            "gain_jitter")
+_ARRAYS = ("goal", "start", "obs_pos", "obs_vel", "obs_rad", "ws_limits")
+
+
+def to_arrays(sc, prefix="in_"):
+    """Flatten a Scenario into numpy arrays (stored inside golden files so that a case built from a
+    reference task YAML can be replayed where /root/reference does not exist)."""
+    d = {prefix + k: np.array(getattr(sc, k)) for k in _SCALARS}
+    d.update({prefix + k: np.array(getattr(sc, k), dtype=np.float64) for k in _ARRAYS})
+    return d
+
+
+def from_arrays(d, prefix="in_"):
+    kw = {}
+    for k in _SCALARS:
+        v = d[prefix + k]
+        v = v.item() if hasattr(v, "item") else v
+        kw[k] = str(v) if k == "name" else v
+    for k in ("num_agents", "max_prediction_steps", "prediction_freq_multiple", "seed"):
+        kw[k] = int(kw[k])
+    kw["feed_obstacles"] = bool(kw["feed_obstacles"])
+    for k in _ARRAYS:
+        kw[k] = np.array(d[prefix + k], dtype=np.float64)
+    return Scenario(**kw)

@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative fp tolerance"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = cases.all_cases()
+CASES = cases.all_cases(GOLDEN)
 REPORT = {}
 
 
@@ -126,6 +126,17 @@ def test_baseline_config_against_oracle(make, ticks):
                  ctx=f"{sc.name}: ")
     # every integration step executes on these workloads
     assert int(got["steps"][-1].sum()) == sc.num_agents * sc.max_prediction_steps
+
+
+@pytest.mark.parametrize("make,ticks", [(scenarios.c3, 2), (lambda: scenarios.c4(8192), 2)])
+def test_full_size_shard_against_oracle(make, ticks):
+    """C3 (4096 x 256 x 500) and one GPU's share of C4 (8192 x 1024 x 200) against the C oracle run on all
+    host threads: every path point, length and distance bit-identical."""
+    sc = make()
+    want = loop.run_closed_loop(_oracle(), sc, ticks, record_paths=True)
+    got = loop.run_closed_loop(_planner(), sc, ticks, record_paths=True)
+    REPORT[sc.name] = _bit_stats(dict(got, final_paths=got["paths"]), dict(want, final_paths=want["paths"]))
+    assert_bit_identical(got, want, ctx=f"{sc.name}: ")
 
 
 def test_c3_full_size_properties():

@@ -12,7 +12,7 @@ from pmaf_b200 import cases, loop, scenarios
 from parity import assert_bit_identical
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = cases.all_cases()
+CASES = cases.all_cases(GOLDEN)
 
 
 def _digest(sc):
