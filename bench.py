@@ -30,7 +30,8 @@ import pmaf_b200  # noqa: E402,F401
 from pmaf_b200 import loop, scenarios  # noqa: E402
 
 METRIC = "agent-prediction-steps/sec"
-WORKLOADS = {"c2": scenarios.c2, "c3": scenarios.c3, "c4": scenarios.c4, "c5": scenarios.c5}
+WORKLOADS = {"c2": scenarios.c2, "c3": scenarios.c3, "c4": scenarios.c4, "c5": scenarios.c5,
+             "c4s": lambda: scenarios.c4(8192)}  # c4s: one GPU's share of C4 (65536 agents over 8 GPUs)
 
 
 def workload_config(sc, n_gpus, extra=None):

@@ -698,9 +698,9 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
   // many warps per SM: the 128-register build keeps 16 warps resident; few: the 255-register build
   int occ = p->tune_occ;
   if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 4 * 148) ? 3 : 1;
-  if (LPA != 32 || block > 128) occ = 1;  // the occupancy builds exist for warp-per-agent CTAs of <= 128 threads
+  if (LPA < 16 || block > 128) occ = 1;  // the occupancy builds exist for 16/32 lanes per agent, CTAs <= 128 threads
   auto kern = dynamic ? rollout_kernel<LPA, true, 1> : rollout_kernel<LPA, false, 1>;
-  if constexpr (LPA == 32) {
+  if constexpr (LPA >= 16) {
     if (occ == 3) kern = dynamic ? rollout_kernel<LPA, true, 3> : rollout_kernel<LPA, false, 3>;
     if (occ == 4) kern = dynamic ? rollout_kernel<LPA, true, 4> : rollout_kernel<LPA, false, 4>;
   }

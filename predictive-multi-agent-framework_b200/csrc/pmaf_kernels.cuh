@@ -314,8 +314,10 @@ struct CandEval {
 // Every in-shell lane also evaluates the tail of attractorForceScaling (:212-226) for ITS obstacle:
 // the chain (sqrt, division, exp; sqrt, division) is independent of the current-vector chain, so the
 // two interleave, and after the closest-obstacle reduction the winner's value is just broadcast.
+//   SPEC: evaluate the scaling speculatively per lane (latency build); otherwise the caller evaluates it
+//   once for the winner after the reduction (throughput builds: fewer instructions).
 #pragma nv_exec_check_disable
-template <bool STATIC_VEL, class M, class G, class Obs, class Known>
+template <bool STATIC_VEL, bool SPEC, class M, class G, class Obs, class Known>
 PMAF_HDT CandEval eval_candidate(M &m, const G &g, const Obs &obs, int n_field, bool active, int i, int type, v3 p,
                                  v3 v, v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat,
                                  const AgentConsts &c, const Known &known, const double *rot_row,
@@ -367,7 +369,7 @@ PMAF_HDT CandEval eval_candidate(M &m, const G &g, const Obs &obs, int n_field, 
       r.rot_i = mk3(0.0, 0.0, 1.0);  // skipped obstacle: its force is discarded below
     }
     // one straight-line block: scaling chain and force chain are independent
-    r.kgs = attractor_scaling(m, goal_vec, sn.dist_goal, p, v, sn.vn, c, r.d, oi);
+    if (SPEC) r.kgs = attractor_scaling(m, goal_vec, sn.dist_goal, p, v, sn.vn, c, r.d, oi);
     const double zr = STATIC_VEL ? sn.zv : dot3(rel, rel);
     const double vel_norm = STATIC_VEL ? sn.vn : m.sqrt_(zr);
     const v3 nv = STATIC_VEL ? nv_static : m.div3_(rel, vel_norm);
@@ -385,7 +387,7 @@ PMAF_HDT CandEval eval_candidate(M &m, const G &g, const Obs &obs, int n_field, 
 // the same evaluation with the built-in IEEE operations, out of line: taken only when some lane's
 // operands fall outside FastMath's range
 #pragma nv_exec_check_disable
-template <bool STATIC_VEL, class G, class Obs, class Known>
+template <bool STATIC_VEL, bool SPEC, class G, class Obs, class Known>
 #if defined(__CUDA_ARCH__)
 __device__ __noinline__
 #else
@@ -396,7 +398,7 @@ inline
                          v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat, const AgentConsts &c,
                          const Known &known, const double *rot_row, const double *random_row) {
   ExactMath em;
-  return eval_candidate<STATIC_VEL>(em, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat, c,
+  return eval_candidate<STATIC_VEL, SPEC>(em, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat, c,
                                     known, rot_row, random_row);
 }
 
@@ -409,7 +411,7 @@ inline
 //   whether an obstacle lies within the shell, and attractorForceScaling's value for the first one
 //   with the smallest dist_obs.
 #pragma nv_exec_check_disable
-template <bool STATIC_VEL, class G, class Obs, class Known>
+template <bool STATIC_VEL, bool SPEC, class G, class Obs, class Known>
 PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t *cand, int n_cand, int type, v3 p,
                          v3 v, v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat,
                          const AgentConsts &c, const Known &known, double *rot_row, const double *random_row,
@@ -426,10 +428,10 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     const bool active = ci < n_cand;
     const int i = active ? (cand ? (int)cand[ci] : ci) : 0;
     FastMath fm;
-    CandEval r = eval_candidate<STATIC_VEL>(fm, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal,
+    CandEval r = eval_candidate<STATIC_VEL, SPEC>(fm, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal,
                                             ghat, c, known, rot_row, random_row);
     if (g.ballot(fm.bad()))
-      r = eval_candidate_exact<STATIC_VEL>(g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat,
+      r = eval_candidate_exact<STATIC_VEL, SPEC>(g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat,
                                            c, known, rot_row, random_row);
     PMAF_T(3);
     // ---- commit ----
@@ -467,9 +469,18 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     const int mine = lci;
     if (shell_ok) g.argmin_reduce_nonneg(lcd, lci);
     else g.argmin_reduce(lcd, lci);
-    // the lane that evaluated the winning obstacle holds its scaling value
-    const unsigned who = g.ballot(mine == lci);
-    kgs_closest = g.bcast(lkgs, PMAF_FFS(who) - 1);
+    if (SPEC) {  // the lane that evaluated the winning obstacle holds its scaling value
+      const unsigned who = g.ballot(mine == lci);
+      kgs_closest = g.bcast(lkgs, PMAF_FFS(who) - 1);
+    } else {  // attractorForceScaling's tail (:212-226) once, for the winner
+      const v3 o_c = obs.pos(lci);
+      FastMath fm;
+      kgs_closest = attractor_scaling(fm, goal_vec, sn.dist_goal, p, v, sn.vn, c, lcd, o_c);
+      if (fm.bad()) {
+        ExactMath em;
+        kgs_closest = attractor_scaling(em, goal_vec, sn.dist_goal, p, v, sn.vn, c, lcd, o_c);
+      }
+    }
   }
   PMAF_T(5);
 }

@@ -30,7 +30,7 @@ struct StepEnv {
 // One integration step of one agent (loop body of cfPrediction, cf_agent.cpp:312-326).
 // Returns the new position in p / velocity in v; updates min_obs.
 #pragma nv_exec_check_disable
-template <bool STATIC_VEL, class G>
+template <bool STATIC_VEL, bool SPEC, class G>
 PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
                          double *fbuf, const KnownBits &known, int type, const AgentConsts &c, v3 init_pos,
                          double *rot_row, const double *random_row, v3 goal_vec, const StepNorms &sn, v3 &p, v3 &v,
@@ -74,7 +74,7 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
       PMAF_T(2);
       double min_d, kgs_closest;
       bool has_closest;
-      field_pass<STATIC_VEL>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat, c, known,
+      field_pass<STATIC_VEL, SPEC>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat, c, known,
                              rot_row, random_row, fbuf, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
       if (min_d < min_obs) min_obs = min_d;
       // `if (force_.norm() > 1e-5) k_goal_scale = attractorForceScaling()` (:319-321); no close obstacle: 1 (:212-214)
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
       has_seg = false;
       if (sn.dist_goal > 0.1 && n_path < max_steps) {  // :310-311
         const v3 prev = p;
-        agent_step<!DYNAMIC>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, sn, p,
+        agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, sn, p,
                              v, min_obs PMAF_T_PASS);
         const v3 seg = sub3(p, prev);
         zseg = dot3(seg, seg), has_seg = true;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
       bool has_closest;
       v3 ghat, nv_unused;
       step_units<false>(em, goal_vec, v, sn, ghat, nv_unused);
-      field_pass<false>(g, obs, n_field, nullptr, n_field, type, p, v, goal_vec, sn, nv_unused, goal, ghat, k, known,
+      field_pass<false, false>(g, obs, n_field, nullptr, n_field, type, p, v, goal_vec, sn, nv_unused, goal, ghat, k, known,
                         R.rot, R.best_random, fbuf, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
       if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
       g.sync();

@@ -56,10 +56,10 @@ extern "C" int hoststep_rollout(int n_obs, const double *obs_pos, const double *
     if (!(sn.dist_goal > 0.1 && n_path < H)) break;
     const v3 prev = p;
     if (dynamic)
-      agent_step<false>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
+      agent_step<false, true>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
                         min_obs);
     else
-      agent_step<true>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
+      agent_step<true, false>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
                        min_obs);
     { const v3 seg = sub3(p, prev); zseg = dot3(seg, seg); has_seg = true; }
     st3(path + 3 * n_path, p);
