@@ -91,6 +91,16 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload):
+    """dram__bytes_read + dram__bytes_write of the rollout kernel, per launch, from the committed
+    `ncu --set full` summary of the same workload (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", f"r01_ncu_rollout_{workload}_summary.json")
+    try:
+        return json.load(open(path)).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def cpu_planner(threads=0):
     from oracle import cpu_planners
 
@@ -246,7 +256,8 @@ def run_ours(args, rank, world, local_rank):
                     "api": "stop_prediction, evaluate_agents, move_real_agent, reset_agents, start_prediction"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": measured_traffic(args.workload) if world == 1 else None,
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "kernel": "rollout_kernel", "kernel_ms": rollout_ms,
                          "kernel_share_of_step": rollout_ms / (dev_ms / args.steps),
                          "note": "the path is FP64-issue/latency bound, not HBM bound (SURVEY.md §8d); "
