@@ -35,8 +35,9 @@ WORKLOADS = {"c2": scenarios.c2, "c3": scenarios.c3, "c4": scenarios.c4, "c5": s
 
 
 def workload_config(sc, n_gpus, extra=None):
+    which = {"c2": "configs[1]", "c3": "configs[2]", "c4": "configs[3]", "c5": "configs[4]"}.get(sc.name[:2], "")
     cfg = {"workload": f"{sc.name}: {sc.num_agents} agents x {sc.num_obstacles} obstacles x horizon "
-                       f"{sc.max_prediction_steps} (BASELINE.json configs[1]), closed dry-run loop, "
+                       f"{sc.max_prediction_steps} (BASELINE.json {which}), closed dry-run loop, "
                        f"{'moving' if sc.feed_obstacles else 'static'} obstacles",
            "agents": sc.num_agents, "obstacles": sc.num_obstacles, "horizon": sc.max_prediction_steps,
            "agents_per_gpu": sc.num_agents // max(n_gpus, 1),
