@@ -430,7 +430,7 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     FastMath fm;
     CandEval r = eval_candidate<STATIC_VEL, SPEC>(fm, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal,
                                             ghat, c, known, rot_row, random_row);
-    if (g.ballot(fm.bad()))
+    if (__builtin_expect(g.ballot(fm.bad()) != 0u, 0))
       r = eval_candidate_exact<STATIC_VEL, SPEC>(g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat,
                                            c, known, rot_row, random_row);
     PMAF_T(3);
@@ -476,7 +476,7 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
       const v3 o_c = obs.pos(lci);
       FastMath fm;
       kgs_closest = attractor_scaling(fm, goal_vec, sn.dist_goal, p, v, sn.vn, c, lcd, o_c);
-      if (fm.bad()) {
+      if (__builtin_expect(fm.bad(), 0)) {
         ExactMath em;
         kgs_closest = attractor_scaling(em, goal_vec, sn.dist_goal, p, v, sn.vn, c, lcd, o_c);
       }

@@ -66,7 +66,7 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
       {
         FastMath fm;
         step_units<STATIC_VEL>(fm, goal_vec, v, sn, ghat, nv_static);
-        if (fm.bad()) {
+        if (__builtin_expect(fm.bad(), 0)) {
           ExactMath em;
           step_units<STATIC_VEL>(em, goal_vec, v, sn, ghat, nv_static);
         }
@@ -86,7 +86,7 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
   const v3 p0 = p, v0 = v, f0 = force;
   FastMath fm;
   finish_step(fm, force, k_goal_scale, sn, o_s, P.pred_dt, c, p, v);
-  if (fm.bad()) {
+  if (__builtin_expect(fm.bad(), 0)) {
     ExactMath em;
     p = p0, v = v0, force = f0;
     finish_step(em, force, k_goal_scale, sn, o_s, P.pred_dt, c, p, v);
@@ -98,7 +98,7 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
 PMAF_HDT StepNorms step_norms_checked(v3 goal_vec, v3 v, double zseg, bool has_seg, const AgentConsts &c) {
   FastMath fm;
   StepNorms sn = step_norms(fm, goal_vec, v, zseg, has_seg, c);
-  if (fm.bad()) {
+  if (__builtin_expect(fm.bad(), 0)) {
     ExactMath em;
     sn = step_norms(em, goal_vec, v, zseg, has_seg, c);
   }
