@@ -186,6 +186,13 @@ int pmaf_get_planned_trajectory(pmaf_planner *p, double *out, int max_points, in
 /* per-(agent, obstacle) latch state: known[(n_agents+1)][n_obs], rot[(n_agents+1)][n_obs][3];
  * the extra last row is the real agent's (cf_agent.h:52-53) */
 int pmaf_get_obstacle_state(pmaf_planner *p, int n_obs, int *known, double *rot);
+/* The k cheapest agents of the last evaluate_agents (ascending cost, lowest index first among equals,
+ * NaN costs last) and their paths decimated to every stride-th point (the last point always kept):
+ * agent_index[k] (-1 where fewer than k agents exist), n_points[k], paths[k][max_points][3]. This is the
+ * batched export for the node's predicted-path markers (node:340-347, 390-427), which otherwise copies
+ * every agent's whole path twice per tick. */
+int pmaf_get_best_paths(pmaf_planner *p, int k, int stride, int max_points, int *agent_index, int *n_points,
+                        double *paths);
 /* costs computed by the last evaluate_agents */
 int pmaf_get_costs(pmaf_planner *p, double *costs /* [n_agents] */);
 

@@ -1330,3 +1330,38 @@ extern "C" int pmaf_get_section_cycles(pmaf_planner *p, long long *out) {
   CU(cudaStreamSynchronize(p->stream));
   return 0;
 }
+
+extern "C" int pmaf_get_best_paths(pmaf_planner *p, int k, int stride, int max_points, int *agent_index, int *n_points,
+                                   double *paths) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(k >= 1 && k <= 64 && stride >= 1 && max_points >= 1 && agent_index && n_points && paths, PMAF_ERR_ARG,
+          "pmaf_get_best_paths: bad argument (1 <= k <= 64, stride >= 1)");
+  REQUIRE(p->have_cost, PMAF_ERR_STATE, "pmaf_get_best_paths: no evaluate_agents yet");
+  if (int rc = finish_rollout(p)) return rc;
+  DevBuf<int> d_idx;
+  CU(d_idx.resize(k));
+  PlannerDev d = make_dev(p);
+  const int threads = p->A >= 1024 ? 1024 : std::max(32, ((p->A + 31) / 32) * 32);
+  if (int rc = launch(p, topk_kernel, dim3(1), dim3(threads), 0, d, k, d_idx.p)) return rc;
+  if (int rc = fetch(p, agent_index, d_idx.p, (size_t)k * sizeof(int))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  d_idx.release();
+  std::vector<double> row((size_t)p->H * 3);
+  for (int r = 0; r < k; ++r) {
+    n_points[r] = 0;
+    const int a = agent_index[r];
+    if (a < 0) continue;
+    int n = 0;
+    if (int rc = fetch(p, &n, p->n_path.p + a, sizeof(int))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    if (int rc = fetch(p, row.data(), p->paths.p + (size_t)a * p->H * 3, (size_t)n * 3 * sizeof(double))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    int m = 0;  // every stride-th point, always including the last one
+    for (int q = 0; q < n && m < max_points; q += stride, ++m) memcpy(paths + ((size_t)r * max_points + m) * 3, &row[3 * (size_t)q], 24);
+    if (n > 0 && (n - 1) % stride != 0 && m < max_points) memcpy(paths + ((size_t)r * max_points + m++) * 3, &row[3 * (size_t)(n - 1)], 24);
+    n_points[r] = m;
+    agent_index[r] = a + p->first_agent;
+  }
+  return 0;
+}

@@ -564,6 +564,45 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   }
 }
 
+// The k cheapest agents of the last evaluate, in (cost, index) order — what the node's predicted-path
+// visualisation needs (panda_bimanual_control.cpp:340-347 draws every path; only these are copied out).
+// One block; k passes of the serial-order argmin, NaN costs last.
+__global__ void __launch_bounds__(1024) topk_kernel(const PlannerDev P, int k, int *out_index) {
+  __shared__ double s_cost[32];
+  __shared__ int s_idx[32];
+  __shared__ double s_last_cost;
+  __shared__ int s_last_idx;
+  if (threadIdx.x == 0) s_last_cost = -(double)INFINITY, s_last_idx = -1;
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    double bc = (double)INFINITY;
+    int bi = 0x7fffffff;
+    const double lc = s_last_cost;
+    const int li = s_last_idx;
+    for (int a = threadIdx.x; a < P.n_agents; a += blockDim.x) {
+      double c = P.cost[a];
+      if (!(c == c)) c = 1.7976931348623157e308;  // NaN costs sort last (they never win the argmin)
+      const bool after = c > lc || (c == lc && a > li);
+      if (after && (c < bc || (c == bc && a < bi))) bc = c, bi = a;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (oc < bc || (oc == bc && oi < bi)) bc = oc, bi = oi;
+    }
+    if ((threadIdx.x & 31) == 0) s_cost[threadIdx.x >> 5] = bc, s_idx[threadIdx.x >> 5] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int nw = (blockDim.x + 31) >> 5;
+      for (int w = 1; w < nw; ++w)
+        if (s_cost[w] < bc || (s_cost[w] == bc && s_idx[w] < bi)) bc = s_cost[w], bi = s_idx[w];
+      out_index[r] = bi == 0x7fffffff ? -1 : bi;
+      s_last_cost = bc, s_last_idx = bi;
+    }
+    __syncthreads();
+  }
+}
+
 // fill rot[A][O][3] with the default (0,0,1) (cf_agent.h:92-96) and clear known bits
 __global__ void init_state_kernel(const PlannerDev P, const double *init_pos) {
   const size_t n = (size_t)P.n_agents * P.n_obs;

@@ -49,7 +49,7 @@ API_SYMBOLS = [
     "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
     "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters",
     "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
-    "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles",
+    "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles", "pmaf_get_best_paths",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library():
     lib.pmaf_get_planned_trajectory.argtypes = [H, _dp, C.c_int, _ip]
     lib.pmaf_get_obstacle_state.argtypes = [H, C.c_int, _ip, _dp]
     lib.pmaf_get_costs.argtypes = [H, _dp]
+    lib.pmaf_get_best_paths.argtypes = [H, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp]
     lib.pmaf_get_counters.argtypes = [H, C.POINTER(Counters)]
     lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int, C.c_int]
     lib.pmaf_set_upload_dedup.argtypes = [H, C.c_int]
@@ -360,3 +361,11 @@ class CfManager:
         out = (C.c_uint64 * 5)()
         self._check(self.lib.pmaf_selftest_math(self.h, int(samples), int(seed), out))
         return dict(zip(("sqrt_mismatch", "div_mismatch", "div3_mismatch", "flagged", "compared"), list(out)))
+
+    def get_best_paths(self, k, stride=1, max_points=None):
+        """The k cheapest agents of the last evaluate and their (decimated) paths."""
+        max_points = int(max_points or self.H)
+        idx, n = np.zeros(k, dtype=np.int32), np.zeros(k, dtype=np.int32)
+        paths = np.full((k, max_points, 3), np.nan)
+        self._check(self.lib.pmaf_get_best_paths(self.h, int(k), int(stride), max_points, _i(idx), _i(n), _d(paths)))
+        return idx, n, paths

@@ -229,3 +229,26 @@ def test_reinit_with_different_sizes_and_many_handles():
         q = CfManager(0)
         loop.plan_begin(q, CASES["single_agent"].scenario)
         q.close()
+
+
+def test_best_k_path_export():
+    """pmaf_get_best_paths: the k cheapest agents in (cost, index) order with decimated paths."""
+    sc = CASES["near326_switching"].scenario
+    p = _planner()
+    feed = loop.ObstacleFeed(sc)
+    loop.plan_begin(p, sc)
+    for _ in range(30):
+        loop.control_tick(p, sc, feed)
+    p.stop_prediction()
+    p.evaluate_agents(feed.pos, feed.vel, feed.rad, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist, sc.k_workspace,
+                      sc.ws_limits)
+    costs, paths, steps = p.get_costs(), p.get_predicted_paths(), p.get_agent_summaries()["steps"]
+    order = sorted(range(len(costs)), key=lambda a: (np.inf if np.isnan(costs[a]) else costs[a], a))
+    idx, n, best = p.get_best_paths(5, stride=7, max_points=40)
+    assert list(idx) == order[:5]
+    for r, a in enumerate(idx):
+        keep = list(range(0, steps[a], 7))
+        if (steps[a] - 1) % 7:
+            keep.append(steps[a] - 1)
+        assert n[r] == len(keep)
+        assert np.array_equal(best[r, : n[r]], paths[a, keep])
