@@ -697,7 +697,9 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
           smem);
   // many warps per SM: the 128-register build keeps 16 warps resident; few: the 255-register build
   int occ = p->tune_occ;
-  if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 4 * 148) ? 3 : 1;
+  // measured on B200: the 255-register latency build wins up to ~8 warps per SM (C5: 1024 agents), the
+  // 170-register build beyond (C3: 4096, C4 shard: 8192 agents)
+  if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 12 * 148) ? 3 : 1;
   if (LPA < 16 || block > 128) occ = 1;  // the occupancy builds exist for 16/32 lanes per agent, CTAs <= 128 threads
   auto kern = dynamic ? rollout_kernel<LPA, true, 1> : rollout_kernel<LPA, false, 1>;
   if constexpr (LPA >= 16) {
