@@ -297,6 +297,24 @@ PMAF_HDT int nearest_other_obstacle(const G &g, const Obs &obs, int n_field, int
   return best_i == 0x7fffffff ? 0 : best_i;
 }
 
+// calculateRotationVector of the agent `type` at first detection (cf_agent.cpp:408-611). Cold code: kept out
+// of the step loop's instruction footprint.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+    v3
+    first_rotation_vector(int type, v3 p, v3 goal, v3 to_obs, v3 oi, v3 o_nn, const double *random_i) {
+  switch (type) {
+    case HAD_HEURISTIC: return rot_had(p, goal, oi);
+    case RANDOM_AGENT: return rot_random(p, goal, ld3(random_i));
+    case OBSTACLE_HEURISTIC: return rot_obstacle(to_obs, oi, o_nn);
+    case GOAL_OBSTACLE_HEURISTIC: return rot_goal_obstacle(p, goal, to_obs, oi, o_nn);
+    default: return mk3(0.0, 0.0, 1.0);  // GOAL :408-412, VEL :539-543
+  }
+}
+
 // What one lane learns about its candidate in one chunk of the narrow phase; nothing is written to
 // memory until the whole group's evaluation is known to be in the arithmetic policy's proven range.
 struct CandEval {
@@ -357,14 +375,8 @@ PMAF_HDT CandEval eval_candidate(M &m, const G &g, const Obs &obs, int n_field, 
     }
   }
   if (r.d < c.shell) {  // candidates of the closest-obstacle search (:201-211), skipped ones included
-    if (r.first_seen) {  // :92-96 (rare: built-in arithmetic)
-      switch (type) {
-        case HAD_HEURISTIC: r.rot_i = rot_had(p, goal, oi); break;
-        case RANDOM_AGENT: r.rot_i = rot_random(p, goal, ld3(random_row + 3 * i)); break;
-        case OBSTACLE_HEURISTIC: r.rot_i = rot_obstacle(to_obs, oi, obs.pos(nn)); break;
-        case GOAL_OBSTACLE_HEURISTIC: r.rot_i = rot_goal_obstacle(p, goal, to_obs, oi, obs.pos(nn)); break;
-        default: r.rot_i = mk3(0.0, 0.0, 1.0); break;  // GOAL :408-412, VEL :539-543
-      }
+    if (__builtin_expect(r.first_seen, 0)) {  // :92-96 (rare, out of line: built-in arithmetic)
+      r.rot_i = first_rotation_vector(type, p, goal, to_obs, oi, obs.pos(nn), random_row + 3 * i);
     } else if (!is_known) {
       r.rot_i = mk3(0.0, 0.0, 1.0);  // skipped obstacle: its force is discarded below
     }

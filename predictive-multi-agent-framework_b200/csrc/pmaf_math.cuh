@@ -107,10 +107,21 @@ PMAF_HD int keep(int x, unsigned runtime_zero) { return x ^ (int)runtime_zero; }
 //              it with ExactMath if the flag is up (zero / tiny / huge / NaN operands: rare).
 //              pmaf_selftest_math compares FastMath with ExactMath on the GPU over random and
 //              adversarial operands (tests/test_gpu_math.py). On the host FastMath is ExactMath.
+// CUDA's IEEE sqrt / division as out-of-line calls: ExactMath only runs on cold paths (re-evaluation of
+// a flagged section, the single real-agent step), and inlining ~40 instructions per operation there
+// bloats the step loop's instruction footprint (the rollout is sensitive to instruction-cache misses).
+#if defined(__CUDA_ARCH__)
+#define PMAF_COLD_FN __device__ __noinline__
+#else
+#define PMAF_COLD_FN inline
+#endif
+PMAF_COLD_FN double cold_sqrt(double x) { return sqrt(x); }
+PMAF_COLD_FN double cold_div(double a, double b) { return a / b; }
+
 struct ExactMath {
-  PMAF_HD double sqrt_(double x) { return sqrt(x); }
-  PMAF_HD double div_(double a, double b) { return a / b; }
-  PMAF_HD v3 div3_(v3 a, double b) { return div3(a, b); }
+  PMAF_HD double sqrt_(double x) { return cold_sqrt(x); }
+  PMAF_HD double div_(double a, double b) { return cold_div(a, b); }
+  PMAF_HD v3 div3_(v3 a, double b) { return mk3(cold_div(a.x, b), cold_div(a.y, b), cold_div(a.z, b)); }
   PMAF_HD bool bad() const { return false; }
 };
 
@@ -256,12 +267,12 @@ PMAF_HD SqThr make_thr(double c) {
 PMAF_HD bool norm_lt(double z, const SqThr &t) {  // sqrt(z) < c
   if (z < t.lo) return true;
   if (z > t.hi) return false;
-  return sqrt(z) < t.c;
+  return cold_sqrt(z) < t.c;
 }
 PMAF_HD bool norm_gt(double z, const SqThr &t) {  // sqrt(z) > c
   if (z > t.hi) return true;
   if (z < t.lo) return false;
-  return sqrt(z) > t.c;
+  return cold_sqrt(z) > t.c;
 }
 
 // Per-agent values the reference recomputes identically every step (same operands, same operation:
@@ -392,13 +403,15 @@ PMAF_HD v3 add_repel_force(v3 force, v3 p, v3 o_s, const AgentConsts &c) {
   const double z = dot3(dv, dv);
   v3 repel = mk3(0.0, 0.0, 0.0);
   if (!(z > c.repel_far2)) {  // otherwise out of the shell for sure: skip the sqrt
-    const double n = sqrt(z);
+    const double n = cold_sqrt(z);
     const double d = clamp_dist(n - c.rsum_s);
-    if (d < c.shell) {
-      const v3 u = normalized_zn(dv, z, n);
-      const double s1 = 1.0 / d - c.inv_shell;
+    if (d < c.shell) {  // rare (self-collision sentinel within reach): out-of-line IEEE operations
+      ExactMath em;
+      const v3 u = normalized_zn_m(em, dv, z, n);
+      const double s1 = cold_div(1.0, d) - c.inv_shell;
       const double s2 = d * d;
-      repel = mk3(c.k_repel * u.x * s1 / s2, c.k_repel * u.y * s1 / s2, c.k_repel * u.z * s1 / s2);
+      repel = mk3(cold_div(c.k_repel * u.x * s1, s2), cold_div(c.k_repel * u.y * s1, s2),
+                  cold_div(c.k_repel * u.z * s1, s2));
     }
   }
   const v3 total = add3(mk3(0.0, 0.0, 0.0), repel);  // total_repel_force += repel_force (:179)
@@ -436,9 +449,10 @@ PMAF_HD double attractor_scaling(M &m, v3 goal_vec, double dist_goal, v3 p, v3 v
 // updatePositionAndVelocity :253-268
 template <class M>
 PMAF_HD void integrate_step(M &m, v3 force, double dt, const AgentConsts &c, v3 &p, v3 &v) {
-  v3 acc = c.unit_mass ? force : div3(force, c.mass);
+  ExactMath em;
+  v3 acc = c.unit_mass ? force : em.div3_(force, c.mass);
   const double zacc = dot3(acc, acc);
-  if (norm_gt(zacc, make_thr(13.0))) acc = mul3(acc, 13.0 / sqrt(zacc));  // rare: exact built-ins
+  if (norm_gt(zacc, make_thr(13.0))) acc = mul3(acc, cold_div(13.0, cold_sqrt(zacc)));  // rare
   const v3 np = mk3((p.x + 0.5 * acc.x * dt * dt) + v.x * dt, (p.y + 0.5 * acc.y * dt * dt) + v.y * dt,
                     (p.z + 0.5 * acc.z * dt * dt) + v.z * dt);
   v = add3(v, mul3(acc, dt));
