@@ -282,7 +282,13 @@ struct KnownBytes {  // the real agent's flags in global memory
 // strict '>' from index 0, start value 100.0, default index 0 — evaluated cooperatively.
 #pragma nv_exec_check_disable
 template <class G, class Obs>
-PMAF_HDT int nearest_other_obstacle(const G &g, const Obs &obs, int n_field, int id) {
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__  // only two agents of a population (OBSTACLE / GOAL_OBSTACLE) ever call it
+#else
+inline
+#endif
+    int
+    nearest_other_obstacle(const G &g, const Obs &obs, int n_field, int id) {
   constexpr int LPA = G::kLanes;
   v3 oi = obs.pos(id);
   double best = 100.0;
@@ -471,16 +477,16 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     }
     PMAF_T(4);
   }
-  // reductions only when they can matter
-  const bool shell_ok = c.shell > 0.0;  // non-negative keys for the integer-ordered reductions
-  if (g.ballot(lmin < (double)INFINITY)) min_d = shell_ok ? g.min_reduce_nonneg(lmin) : g.min_reduce(lmin);
+  // reductions only when they can matter. All keys are non-negative (dist_obs >= 1e-5; a lane without a
+  // close obstacle holds the shell radius, and has_closest implies shell > 1e-5), so the integer-ordered
+  // redux reductions apply.
+  if (g.ballot(lmin < (double)INFINITY)) min_d = g.min_reduce_nonneg(lmin);
   else min_d = (double)INFINITY;
   has_closest = g.ballot(lci != 0x7fffffff) != 0u;
   kgs_closest = 1.0;
   if (has_closest) {
     const int mine = lci;
-    if (shell_ok) g.argmin_reduce_nonneg(lcd, lci);
-    else g.argmin_reduce(lcd, lci);
+    g.argmin_reduce_nonneg(lcd, lci);
     if (SPEC) {  // the lane that evaluated the winning obstacle holds its scaling value
       const unsigned who = g.ballot(mine == lci);
       kgs_closest = g.bcast(lkgs, PMAF_FFS(who) - 1);

@@ -117,6 +117,7 @@ PMAF_HD int keep(int x, unsigned runtime_zero) { return x ^ (int)runtime_zero; }
 #endif
 PMAF_COLD_FN double cold_sqrt(double x) { return sqrt(x); }
 PMAF_COLD_FN double cold_div(double a, double b) { return a / b; }
+PMAF_COLD_FN double cold_exp(double x) { return exp(x); }
 
 struct ExactMath {
   PMAF_HD double sqrt_(double x) { return cold_sqrt(x); }
@@ -229,7 +230,7 @@ PMAF_HD double exp_glibc(double x) {
   // main path of __exp: 2^-54 <= |x| < 512 (no special-casing of the scale needed)
   if (abstop - 0x3c9u >= 0x408u - 0x3c9u) {
     if (abstop < 0x3c9u) return 1.0 + x;  // tiny |x| (WANT_ROUNDING)
-    return exp(x);                         // |x| >= 512, inf, nan: outside the planner's domain
+    return cold_exp(x);                    // |x| >= 512, inf, nan: outside the planner's domain
   }
   double kd = fma(kExpInvLn2N, x, kExpShift);
   const uint64_t ki = bits_of(kd);
