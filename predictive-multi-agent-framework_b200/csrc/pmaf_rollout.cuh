@@ -27,43 +27,111 @@ struct StepEnv {
   double pred_dt;
 };
 
+// ---- broad phase: fp32 sphere test, ordered compaction of candidate indices into cand[] --------------
+// Straight-line version for up to ROUNDS * kLanes field obstacles (no branch: it is meant to sit in the
+// same basic block as the prologue's FP64 chains so that the scheduler interleaves them).
+#pragma nv_exec_check_disable
+template <int ROUNDS, class G>
+PMAF_HDT int broad_phase_unrolled(const G &g, const float4 *bp, int n_field, v3 p, uint16_t *cand) {
+  constexpr int LPA = G::kLanes;
+  const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
+  const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
+  int n_cand = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int i = r * LPA + g.gl;
+    const bool in_range = i < n_field;
+    const float4 b = bp[in_range ? i : 0];
+    const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
+    const bool cnd = in_range && dx * dx + dy * dy + dz * dz < b.w;
+    const unsigned m = g.ballot(cnd);
+    if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
+    n_cand += PMAF_POPC(m);
+  }
+  return n_cand;
+}
+#pragma nv_exec_check_disable
+template <class G>
+PMAF_HDT int broad_phase_loop(const G &g, const float4 *bp, int n_field, v3 p, uint16_t *cand) {
+  constexpr int LPA = G::kLanes;
+  const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
+  const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
+  int n_cand = 0;
+  for (int base = 0; base < n_field; base += LPA) {
+    const int i = base + g.gl;
+    bool cnd = false;
+    if (i < n_field) {
+      const float4 b = bp[i];
+      const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
+      cnd = dx * dx + dy * dy + dz * dz < b.w;
+    }
+    const unsigned m = g.ballot(cnd);
+    if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
+    n_cand += PMAF_POPC(m);
+  }
+  return n_cand;
+}
+
+// Step prologue: everything that depends only on (p, v) — the norms, the unit vectors the field pass
+// needs, attractorForce's desired velocity and, for small obstacle sets, the broad phase — in ONE
+// basic block: five independent sqrt/division chains plus the fp32/integer broad phase interleave
+// instead of running back to back (a single warp issues in order; only the compiler's scheduling inside
+// a block overlaps them). The broad phase is speculative (its only side effect is the scratch list).
+struct Prologue {
+  StepNorms sn;
+  v3 ghat, nv_static;
+  int n_cand;  // -1: broad phase not done yet (large obstacle sets)
+};
+constexpr int kBroadUnrolledRounds = 2;
+#pragma nv_exec_check_disable
+// EAGER (latency build): unit vectors and broad phase are evaluated speculatively here; otherwise
+// (throughput builds) only the norms, and the rest on demand in agent_step — fewer instructions.
+template <bool STATIC_VEL, bool EAGER, class G>
+PMAF_HDT Prologue step_prologue(const G &g, const float4 *bp, int n_field, uint16_t *cand, v3 goal_vec, v3 p, v3 v,
+                                double zseg, bool has_seg, const AgentConsts &c) {
+  Prologue pr;
+  FastMath fm;
+  pr.sn = step_norms(fm, goal_vec, v, zseg, has_seg, c);
+  pr.n_cand = -1;
+  pr.ghat = pr.nv_static = mk3(0.0, 0.0, 0.0);
+  if (EAGER) {
+    step_units<STATIC_VEL>(fm, goal_vec, v, pr.sn, pr.ghat, pr.nv_static);
+    const bool small = n_field <= kBroadUnrolledRounds * G::kLanes;
+    pr.n_cand = broad_phase_unrolled<kBroadUnrolledRounds>(g, bp, small ? n_field : 0, p, cand);
+    if (!small) pr.n_cand = -1;
+  }
+  if (__builtin_expect(fm.bad(), 0)) {
+    ExactMath em;
+    pr.sn = step_norms(em, goal_vec, v, zseg, has_seg, c);
+    if (EAGER) step_units<STATIC_VEL>(em, goal_vec, v, pr.sn, pr.ghat, pr.nv_static);
+  }
+  return pr;
+}
+
 // One integration step of one agent (loop body of cfPrediction, cf_agent.cpp:312-326).
 // Returns the new position in p / velocity in v; updates min_obs.
 #pragma nv_exec_check_disable
 template <bool STATIC_VEL, bool SPEC, class G>
 PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs, const float4 *bp, uint16_t *cand,
                          double *fbuf, const KnownBits &known, int type, const AgentConsts &c, v3 init_pos,
-                         double *rot_row, const double *random_row, v3 goal_vec, const StepNorms &sn, v3 &p, v3 &v,
+                         double *rot_row, const double *random_row, v3 goal_vec, const Prologue &pr, v3 &p, v3 &v,
                          double &min_obs PMAF_T_ARGS) {
-  constexpr int LPA = G::kLanes;
+  const StepNorms &sn = pr.sn;
   const v3 goal = P.goal;
   const int n_field = P.n_obs - 1;  // the sentinel is excluded from the field loops (:75)
   v3 force = mk3(0.0, 0.0, 0.0);    // resetForce()
   double k_goal_scale = 1.0;
   if (field_gate_open(sn.dist_goal, sn.vn, p, init_pos, c)) {
     PMAF_T(8);
-    // ---- broad phase: fp32 sphere test, ordered compaction of candidate indices ----
-    const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
-    const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
-    int n_cand = 0;
-    for (int base = 0; base < n_field; base += LPA) {
-      const int i = base + g.gl;
-      bool cnd = false;
-      if (i < n_field) {
-        const float4 b = bp[i];
-        const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
-        cnd = dx * dx + dy * dy + dz * dz < b.w;
-      }
-      const unsigned m = g.ballot(cnd);
-      if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
-      n_cand += PMAF_POPC(m);
-    }
+    const int n_cand = pr.n_cand >= 0 ? pr.n_cand : broad_phase_loop(g, bp, n_field, p, cand);
     PMAF_T(1);
     if (n_cand > 0) {
       g.sync();
       // ---- narrow phase ----
-      v3 ghat, nv_static;
-      {
+      v3 ghat = pr.ghat, nv_static = pr.nv_static;
+      if (!SPEC) {  // throughput builds: unit vectors on demand
         FastMath fm;
         step_units<STATIC_VEL>(fm, goal_vec, v, sn, ghat, nv_static);
         if (__builtin_expect(fm.bad(), 0)) {
@@ -71,17 +139,17 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
           step_units<STATIC_VEL>(em, goal_vec, v, sn, ghat, nv_static);
         }
       }
-      PMAF_T(2);
       double min_d, kgs_closest;
       bool has_closest;
-      field_pass<STATIC_VEL, SPEC>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat, c, known,
-                             rot_row, random_row, fbuf, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
+      field_pass<STATIC_VEL, SPEC>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat,
+                                   c, known, rot_row, random_row, fbuf, force, min_d, has_closest,
+                                   kgs_closest PMAF_T_PASS);
       if (min_d < min_obs) min_obs = min_d;
       // `if (force_.norm() > 1e-5) k_goal_scale = attractorForceScaling()` (:319-321); no close obstacle: 1 (:212-214)
       if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
-      g.sync();  // cand[] is rewritten by the next step's broad phase
     }
   }
+  g.sync();  // cand[] is rewritten by the next step's (speculative) broad phase
   const v3 o_s = obs.pos(P.n_obs - 1);
   const v3 p0 = p, v0 = v, f0 = force;
   FastMath fm;
@@ -92,17 +160,6 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
     finish_step(em, force, k_goal_scale, sn, o_s, P.pred_dt, c, p, v);
   }
   PMAF_T(6);
-}
-
-// step prologue under FastMath with the exact re-evaluation
-PMAF_HDT StepNorms step_norms_checked(v3 goal_vec, v3 v, double zseg, bool has_seg, const AgentConsts &c) {
-  FastMath fm;
-  StepNorms sn = step_norms(fm, goal_vec, v, zseg, has_seg, c);
-  if (__builtin_expect(fm.bad(), 0)) {
-    ExactMath em;
-    sn = step_norms(em, goal_vec, v, zseg, has_seg, c);
-  }
-  return sn;
 }
 
 // Rollout of every agent to termination. Each group continues ITS agent from the agent's current
@@ -203,14 +260,15 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   for (;;) {
     if (alive) {
       const v3 goal_vec = sub3(goal, p);
-      const StepNorms sn = step_norms_checked(goal_vec, v, zseg, has_seg, k);
+      const Prologue pr = step_prologue<!DYNAMIC, OCC == 1>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zseg, has_seg, k);
+      const StepNorms &sn = pr.sn;
       PMAF_T(0);
       path_len += sn.seg_len;  // getPathLength term (:29), in path order
       has_seg = false;
       if (sn.dist_goal > 0.1 && n_path < max_steps) {  // :310-311
         const v3 prev = p;
-        agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, sn, p,
-                             v, min_obs PMAF_T_PASS);
+        agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row,
+                                       goal_vec, pr, p, v, min_obs PMAF_T_PASS);
         const v3 seg = sub3(p, prev);
         zseg = dot3(seg, seg), has_seg = true;
         if (fused) ws_cost = add_workspace_cost(ws_cost, p, wsp.ws, wsp.k_workspace);

@@ -50,16 +50,18 @@ extern "C" int hoststep_rollout(int n_obs, const double *obs_pos, const double *
   bool has_seg = false;
   for (;;) {
     const v3 goal_vec = sub3(gl, p);
-    const StepNorms sn = step_norms_checked(goal_vec, v, zseg, has_seg, k);
+    const Prologue pr = dynamic ? step_prologue<false, true>(g, bp.data(), n_obs - 1, cand.data(), goal_vec, p, v, zseg, has_seg, k)
+                                : step_prologue<true, false>(g, bp.data(), n_obs - 1, cand.data(), goal_vec, p, v, zseg, has_seg, k);
+    const StepNorms &sn = pr.sn;
     path_len += sn.seg_len;
     has_seg = false;
     if (!(sn.dist_goal > 0.1 && n_path < H)) break;
     const v3 prev = p;
     if (dynamic)
-      agent_step<false, true>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
+      agent_step<false, true>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, pr, p, v,
                         min_obs);
     else
-      agent_step<true, false>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, sn, p, v,
+      agent_step<true, false>(g, P, obs, bp.data(), cand.data(), fbuf, known, type, k, ip, rot_io, random_vecs, goal_vec, pr, p, v,
                        min_obs);
     { const v3 seg = sub3(p, prev); zseg = dot3(seg, seg); has_seg = true; }
     st3(path + 3 * n_path, p);
