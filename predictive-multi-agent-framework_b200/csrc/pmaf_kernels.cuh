@@ -433,7 +433,8 @@ template <bool STATIC_VEL, bool SPEC, class G, class Obs, class Known>
 PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t *cand, int n_cand, int type, v3 p,
                          v3 v, v3 goal_vec, const StepNorms &sn, v3 nv_static, v3 goal, v3 ghat,
                          const AgentConsts &c, const Known &known, double *rot_row, const double *random_row,
-                         double *fbuf, v3 &force, double &min_d, bool &has_closest, double &kgs_closest PMAF_T_ARGS) {
+                         double *fbuf, double min_obs, v3 &force, double &min_d, bool &has_closest,
+                         double &kgs_closest PMAF_T_ARGS) {
   constexpr int LPA = G::kLanes;
   force = mk3(0.0, 0.0, 0.0);
   double lmin = (double)INFINITY;
@@ -470,9 +471,20 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
       }
       g.sync();
       const int n_contrib = PMAF_POPC(contrib);
-      for (int j = 0; j < n_contrib; ++j) {
-        force.x += fbuf[3 * j], force.y += fbuf[3 * j + 1], force.z += fbuf[3 * j + 2];
+      // software-pipelined by two: the loads of the next pair are in flight while the current pair is added
+      // (the adds are serially dependent, the loads are not)
+      v3 a = mk3(fbuf[0], fbuf[1], fbuf[2]);
+      v3 b = n_contrib > 1 ? mk3(fbuf[3], fbuf[4], fbuf[5]) : mk3(0.0, 0.0, 0.0);
+      int j = 0;
+      for (; j + 2 <= n_contrib; j += 2) {
+        const int j2 = j + 2 < n_contrib ? j + 2 : 0, j3 = j + 3 < n_contrib ? j + 3 : 0;
+        const v3 na = mk3(fbuf[3 * j2], fbuf[3 * j2 + 1], fbuf[3 * j2 + 2]);
+        const v3 nb = mk3(fbuf[3 * j3], fbuf[3 * j3 + 1], fbuf[3 * j3 + 2]);
+        force = add3(force, a);
+        force = add3(force, b);
+        a = na, b = nb;
       }
+      if (j < n_contrib) force = add3(force, a);
       g.sync();
     }
     PMAF_T(4);
@@ -480,7 +492,8 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
   // reductions only when they can matter. All keys are non-negative (dist_obs >= 1e-5; a lane without a
   // close obstacle holds the shell radius, and has_closest implies shell > 1e-5), so the integer-ordered
   // redux reductions apply.
-  if (g.ballot(lmin < (double)INFINITY)) min_d = g.min_reduce_nonneg(lmin);
+  // min_obs = the agent's running minimum: the reduction is skipped when no lane can lower it
+  if (g.ballot(lmin < min_obs)) min_d = g.min_reduce_nonneg(lmin);
   else min_d = (double)INFINITY;
   has_closest = g.ballot(lci != 0x7fffffff) != 0u;
   kgs_closest = 1.0;

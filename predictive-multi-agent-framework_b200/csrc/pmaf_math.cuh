@@ -518,6 +518,10 @@ PMAF_HD WsParams pin_ws(const double *ws, double k_workspace, unsigned z) {
   return w;
 }
 PMAF_HD double add_workspace_cost(double cost, v3 q, const double *ws, double k_workspace) {
+  // one combined test first: a point inside the workspace (the common case) costs six independent
+  // compares and a single branch instead of six dependent compare-and-branch pairs
+  const bool outside = (q.x > ws[0]) | (q.x < ws[1]) | (q.y > ws[2]) | (q.y < ws[3]) | (q.z > ws[4]) | (q.z < ws[5]);
+  if (!outside) return cost;
   double t;
   if (q.x > ws[0]) {
     t = fabs(q.x - ws[0]) * k_workspace;

@@ -142,7 +142,7 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
       double min_d, kgs_closest;
       bool has_closest;
       field_pass<STATIC_VEL, SPEC>(g, obs, n_field, cand, n_cand, type, p, v, goal_vec, sn, nv_static, goal, ghat,
-                                   c, known, rot_row, random_row, fbuf, force, min_d, has_closest,
+                                   c, known, rot_row, random_row, fbuf, min_obs, force, min_d, has_closest,
                                    kgs_closest PMAF_T_PASS);
       if (min_d < min_obs) min_obs = min_d;
       // `if (force_.norm() > 1e-5) k_goal_scale = attractorForceScaling()` (:319-321); no close obstacle: 1 (:212-214)
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
       v3 ghat, nv_unused;
       step_units<false>(em, goal_vec, v, sn, ghat, nv_unused);
       field_pass<false, false>(g, obs, n_field, nullptr, n_field, type, p, v, goal_vec, sn, nv_unused, goal, ghat, k, known,
-                        R.rot, R.best_random, fbuf, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
+                        R.rot, R.best_random, fbuf, 0.0, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
       if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
       g.sync();
     }
