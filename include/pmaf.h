@@ -212,6 +212,9 @@ typedef struct {
   int grid_blocks;
   int smem_bytes;
   int occupancy_build;
+  int reserved_;
+  uint64_t general_steps_total; /* steps of all completed rollouts that took the general (branchy) step
+                                 * instead of the straight-line one (latency build; csrc/pmaf_fast.cuh) */
 } pmaf_counters;
 int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out);
 /* rollout kernel shape override for experiments: lanes_per_agent in {0 (auto), 4, 8, 16, 32};

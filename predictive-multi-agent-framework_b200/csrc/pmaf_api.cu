@@ -71,7 +71,7 @@ struct HostOut {  // pinned D2H landing zone
   EvalResult eval;
   DeviceBest best;
   RealState real;
-  unsigned long long steps[2];
+  unsigned long long steps[4];
   double real_path[256 * 3];
 };
 
@@ -361,7 +361,7 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(p->eval.resize(1));
   CU(p->rec.resize(argmin_record_bytes(0)));
   CU(p->real.resize(1));
-  CU(p->step_counter.resize(2));
+  CU(p->step_counter.resize(4));
   CU(p->scratch.resize(16));
   CU(p->runtime_zero.resize(1));
   CU(cudaMemsetAsync(p->runtime_zero.p, 0, sizeof(unsigned), p->stream));
@@ -371,7 +371,7 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
 #endif
   CU(cudaMemsetAsync(p->best.p, 0, sizeof(DeviceBest), p->stream));
   CU(cudaMemsetAsync(p->real.p, 0, sizeof(RealState), p->stream));
-  CU(cudaMemsetAsync(p->step_counter.p, 0, 2 * sizeof(unsigned long long), p->stream));
+  CU(cudaMemsetAsync(p->step_counter.p, 0, 4 * sizeof(unsigned long long), p->stream));
   CU(cudaStreamSynchronize(p->stream));
   *out = p;
   return 0;
@@ -1125,10 +1125,11 @@ extern "C" int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out) {
   REQUIRE(out, PMAF_ERR_ARG, "null output");
   if (p->initialized) {
     if (int rc = finish_rollout(p)) return rc;
-    if (int rc = fetch(p, p->h_out->steps, p->step_counter.p, 2 * sizeof(unsigned long long))) return rc;
+    if (int rc = fetch(p, p->h_out->steps, p->step_counter.p, 4 * sizeof(unsigned long long))) return rc;
     CU(cudaStreamSynchronize(p->stream));
     p->ctr.agent_steps = p->h_out->steps[0];
     p->ctr.agent_steps_total = p->h_out->steps[1];
+    p->ctr.general_steps_total = p->h_out->steps[2];
   }
   *out = p->ctr;
   return 0;
@@ -1294,7 +1295,22 @@ __global__ void math_selftest_kernel(unsigned long long seed, int iters, unsigne
                __double_as_longlong(got.z) != __double_as_longlong(num.z / b))
         ++bad_div3;
     }
-    compared += 3;
+    {  // fused root + reciprocal of the root (normalisations of the straight-line step)
+      FastMath fm;
+      double s_, y_;
+      fm.sqrt_rcp_(x, s_, y_);
+      const v3 num = mk3(b, 0.37 * a, -s_);
+      const v3 got = fm.quot3_(num, s_, y_);
+      if (fm.bad()) ++flagged;
+      else {
+        if (__double_as_longlong(s_) != __double_as_longlong(sqrt(x))) ++bad_sqrt;
+        if (__double_as_longlong(got.x) != __double_as_longlong(num.x / s_) ||
+            __double_as_longlong(got.y) != __double_as_longlong(num.y / s_) ||
+            __double_as_longlong(got.z) != __double_as_longlong(num.z / s_))
+          ++bad_div3;
+      }
+    }
+    compared += 4;
   }
   atomicAdd(out + 0, bad_sqrt), atomicAdd(out + 1, bad_div), atomicAdd(out + 2, bad_div3);
   atomicAdd(out + 3, flagged), atomicAdd(out + 4, compared);

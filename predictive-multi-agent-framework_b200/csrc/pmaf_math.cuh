@@ -179,10 +179,38 @@ struct FastMath {
     const double y = rcp_(b);
     return mk3(quot_(a.x, b, y), quot_(a.y, b, y), quot_(a.z, b, y));
   }
+  __device__ __forceinline__ v3 quot3_(v3 a, double b, double y) {
+    return mk3(quot_(a.x, b, y), quot_(a.y, b, y), quot_(a.z, b, y));
+  }
+  // s = RN(sqrt(x)) and y ~ 1/s to within an ulp for x in [2^-600, 2^600): the Goldschmidt iteration of
+  // sqrt_ already carries h ~ 1/(2 sqrt(x)), so the reciprocal of the root costs one Newton step on 2h
+  // instead of a second MUFU seed and two steps — a normalisation (sqrt, then three divisions by the
+  // root) is five dependent operations shorter. s is in [2^-300, 2^300] by construction: no range check.
+  __device__ __forceinline__ void sqrt_rcp_(double x, double &s, double &y) {
+    need_range(x, -600, 600);
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double g = x * y0, h = 0.5 * y0;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g), h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g), h = fma(h, r, h);
+    const double d = fma(-g, g, x);  // exact residual
+    s = fma(d, h, g);
+    const double y2 = h + h;
+    const double e = fma(-s, y2, 1.0);
+    y = fma(y2, e, y2);
+  }
 #else
   double sqrt_(double x) { return sqrt(x); }
   double div_(double a, double b) { return a / b; }
   v3 div3_(v3 a, double b) { return div3(a, b); }
+  // host stand-ins (y is unused: the host divides)
+  void need_range(double, int, int) {}
+  double rcp_(double b) { return 1.0 / b; }
+  double quot_(double a, double b, double) { return a / b; }
+  v3 quot3_(v3 a, double b, double) { return div3(a, b); }
+  void sqrt_rcp_(double x, double &s, double &y) { s = sqrt(x), y = 1.0 / s; }
 #endif
 };
 

@@ -5,16 +5,19 @@
 
 namespace pmaf {
 
+// contributions the straight-line step (pmaf_fast.cuh) sums without a loop: the staging buffer is zero-padded by this many slots
+constexpr int kFastSumUnroll = 8;
+
 // Shared memory of a rollout CTA:
 //   [0, 16)                      mbarrier
 //   [16, 16 + img.bytes)         obstacle image (TMA bulk copy of PlannerDev::image)
-//   then per group: double fbuf[3 * LPA] (ordered force sum staging), uint16 cand[cand_stride],
+//   then per group: double fbuf[3 * (LPA + 8)] (ordered force sum staging), uint16 cand[cand_stride],
 //   uint32 known[known_words]
 __host__ __device__ inline uint32_t rollout_cand_stride(int n_obs) { return (uint32_t)((n_obs + 7) & ~7); }
 __host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, int groups, int lanes_per_agent,
                                                      int known_words) {
   size_t b = 16 + img.bytes;
-  b += (size_t)groups * 3 * lanes_per_agent * sizeof(double);
+  b += (size_t)groups * 3 * (lanes_per_agent + kFastSumUnroll) * sizeof(double);
   b += (size_t)groups * rollout_cand_stride(img.n_obs) * sizeof(uint16_t);
   b += (size_t)groups * known_words * sizeof(uint32_t);
   return (b + 15) & ~(size_t)15;
@@ -110,6 +113,10 @@ PMAF_HDT Prologue step_prologue(const G &g, const float4 *bp, int n_field, uint1
   return pr;
 }
 
+}  // namespace pmaf
+#include "pmaf_fast.cuh"
+namespace pmaf {
+
 // One integration step of one agent (loop body of cfPrediction, cf_agent.cpp:312-326).
 // Returns the new position in p / velocity in v; updates min_obs.
 #pragma nv_exec_check_disable
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   unsigned char *img = smem + 16;
   const int groups = blockDim.x / LPA;
   double *fbuf_all = reinterpret_cast<double *>(img + P.img.bytes);
-  uint16_t *cand_all = reinterpret_cast<uint16_t *>(fbuf_all + (size_t)groups * 3 * LPA);
+  uint16_t *cand_all = reinterpret_cast<uint16_t *>(fbuf_all + (size_t)groups * 3 * (LPA + kFastSumUnroll));
   const uint32_t cand_stride = rollout_cand_stride(P.n_obs);
   uint32_t *known_all = reinterpret_cast<uint32_t *>(cand_all + (size_t)groups * cand_stride);
 
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   const int a = blockIdx.x * groups + group_in_block;  // local agent index
   const bool have_agent = a < P.n_agents;
   uint16_t *cand = cand_all + (size_t)group_in_block * cand_stride;
-  double *fbuf = fbuf_all + (size_t)group_in_block * 3 * LPA;
+  double *fbuf = fbuf_all + (size_t)group_in_block * 3 * (LPA + kFastSumUnroll);
   KnownBits known;
   known.w = known_all + (size_t)group_in_block * P.known_words;
 
@@ -249,8 +256,12 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   const int max_steps = keep(P.max_steps, rz);
   const bool fused = keep(P.fused_valid, rz) != 0;
   const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace, rz);
+  // latency build, one warp per agent: common steps take the straight-line path (pmaf_fast.cuh)
+  constexpr bool FAST = OCC == 1 && LPA == 32;
+  FastConsts fc;
+  if (FAST) fc = make_fast_consts(k, rz);
   const unsigned long long t0 = global_timer_ns();
-  int steps_run = 0;
+  int steps_run = 0, general_steps = 0;
   bool alive = have_agent;
   double *path_row = have_agent ? P.paths + (size_t)a * P.max_steps * 3 : nullptr;
 
@@ -267,8 +278,15 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
       has_seg = false;
       if (sn.dist_goal > 0.1 && n_path < max_steps) {  // :310-311
         const v3 prev = p;
-        agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row,
-                                       goal_vec, pr, p, v, min_obs PMAF_T_PASS);
+        bool done = false;
+        if constexpr (FAST)
+          done = fast_step<!DYNAMIC>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, goal_vec, pr, p, v,
+                                     min_obs);
+        if (!done) {
+          ++general_steps;
+          agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row,
+                                         goal_vec, pr, p, v, min_obs PMAF_T_PASS);
+        }
         const v3 seg = sub3(p, prev);
         zseg = dot3(seg, seg), has_seg = true;
         if (fused) ws_cost = add_workspace_cost(ws_cost, p, wsp.ws, wsp.k_workspace);
@@ -322,6 +340,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         P.reached[a] = norm3(sub3(goal, p)) < 0.100001 ? 1 : 0;
         atomicAdd(P.step_counter, (unsigned long long)steps_run);
         atomicAdd(P.step_counter + 1, (unsigned long long)steps_run);
+        atomicAdd(P.step_counter + 2, (unsigned long long)general_steps);
       }
     }
   }

@@ -34,7 +34,8 @@ class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("collectives", C.c_uint64), ("rollouts", C.c_uint64), ("agent_steps", C.c_uint64), ("agent_steps_total", C.c_uint64),
                 ("last_rollout_ms", C.c_double), ("rollout_ms_total", C.c_double), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("lanes_per_agent", C.c_int), ("block_threads", C.c_int),
-                ("grid_blocks", C.c_int), ("smem_bytes", C.c_int), ("occupancy_build", C.c_int)]
+                ("grid_blocks", C.c_int), ("smem_bytes", C.c_int), ("occupancy_build", C.c_int), ("reserved_", C.c_int),
+                ("general_steps_total", C.c_uint64)]
 
 
 # every symbol include/pmaf.h declares (tests check that the library exports all of them)
