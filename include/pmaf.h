@@ -217,6 +217,12 @@ typedef struct {
                                  * instead of the straight-line one (latency build; csrc/pmaf_fast.cuh) */
 } pmaf_counters;
 int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out);
+/* Developer instrumentation (libraries built with -DPMAF_FAST_STATS, all zero otherwise): how many steps
+ * each reason kept off the straight-line step since create — out[0] unusable / candidate count, [1] start
+ * radius threshold, [2] range flag (distance chain), [3] first detection needing the general latch,
+ * [4] range flag (force chain), [5] |F| threshold, [6] sentinel in reach, [7] acceleration clamp,
+ * [8] range flag (integrator). Call after pmaf_get_counters. */
+int pmaf_get_fast_stats(pmaf_planner *p, uint64_t out[12]);
 /* rollout kernel shape override for experiments: lanes_per_agent in {0 (auto), 4, 8, 16, 32};
  * block_threads 0 (auto) or a multiple of 32 up to 256; occupancy 0 (auto), 1, 3 or 4 = resident CTAs
  * per SM the kernel's register budget is compiled for (255 / 170 / 128 registers per thread). */

@@ -71,7 +71,7 @@ struct HostOut {  // pinned D2H landing zone
   EvalResult eval;
   DeviceBest best;
   RealState real;
-  unsigned long long steps[4];
+  unsigned long long steps[16];
   double real_path[256 * 3];
 };
 
@@ -361,7 +361,7 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(p->eval.resize(1));
   CU(p->rec.resize(argmin_record_bytes(0)));
   CU(p->real.resize(1));
-  CU(p->step_counter.resize(4));
+  CU(p->step_counter.resize(16));
   CU(p->scratch.resize(16));
   CU(p->runtime_zero.resize(1));
   CU(cudaMemsetAsync(p->runtime_zero.p, 0, sizeof(unsigned), p->stream));
@@ -371,7 +371,7 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
 #endif
   CU(cudaMemsetAsync(p->best.p, 0, sizeof(DeviceBest), p->stream));
   CU(cudaMemsetAsync(p->real.p, 0, sizeof(RealState), p->stream));
-  CU(cudaMemsetAsync(p->step_counter.p, 0, 4 * sizeof(unsigned long long), p->stream));
+  CU(cudaMemsetAsync(p->step_counter.p, 0, 16 * sizeof(unsigned long long), p->stream));
   CU(cudaStreamSynchronize(p->stream));
   *out = p;
   return 0;
@@ -1125,13 +1125,22 @@ extern "C" int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out) {
   REQUIRE(out, PMAF_ERR_ARG, "null output");
   if (p->initialized) {
     if (int rc = finish_rollout(p)) return rc;
-    if (int rc = fetch(p, p->h_out->steps, p->step_counter.p, 4 * sizeof(unsigned long long))) return rc;
+    if (int rc = fetch(p, p->h_out->steps, p->step_counter.p, 16 * sizeof(unsigned long long))) return rc;
     CU(cudaStreamSynchronize(p->stream));
     p->ctr.agent_steps = p->h_out->steps[0];
     p->ctr.agent_steps_total = p->h_out->steps[1];
     p->ctr.general_steps_total = p->h_out->steps[2];
   }
   *out = p->ctr;
+  return 0;
+}
+
+// Developer statistics (libraries built with -DPMAF_FAST_STATS): how often each reason sent a step of the
+// latency build to the general step; out[12], all zero otherwise. Call after pmaf_get_counters.
+extern "C" int pmaf_get_fast_stats(pmaf_planner *p, uint64_t out[12]) {
+  ENTER(p);
+  REQUIRE(out, PMAF_ERR_ARG, "null output");
+  for (int i = 0; i < 12; ++i) out[i] = p->h_out->steps[4 + i];
   return 0;
 }
 

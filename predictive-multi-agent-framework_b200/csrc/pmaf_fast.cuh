@@ -28,16 +28,25 @@ struct FastConsts {   // per-agent loop invariants of the fast step
   SqThr thr_acc;      // |a| > 13   (:256)
   SqThr thr_start;    // |p - p0| < 0.2 (:316)
   bool usable;        // unit mass, shell inside FastMath's range
+  int tbits;          // kT* bits of the agent's type (opaque to the compiler: no re-derivation from `type`)
 };
+constexpr int kTUsesRot = 1, kTRandom = 2, kTGoal = 4, kTVel = 8, kTNeedsNN = 16;
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ FastConsts make_fast_consts(const AgentConsts &c, unsigned rz) {
+__device__ __forceinline__ FastConsts make_fast_consts(const AgentConsts &c, int type, unsigned rz) {
   FastConsts f;
+  int tb = 0;
+  if (type != GOAL_HEURISTIC && type != VEL_HEURISTIC) tb |= kTUsesRot;
+  if (type == RANDOM_AGENT) tb |= kTRandom;
+  if (type == GOAL_HEURISTIC) tb |= kTGoal;
+  if (type == VEL_HEURISTIC) tb |= kTVel;
+  if (type == OBSTACLE_HEURISTIC || type == GOAL_OBSTACLE_HEURISTIC) tb |= kTNeedsNN;
+  f.tbits = keep(tb, rz);
   FastMath m;
   f.y_shell = keep(m.rcp_(c.shell), rz);
   f.thr_force = make_thr(1e-5), f.thr_acc = make_thr(13.0), f.thr_start = make_thr(0.2);
   f.thr_force.lo = keep(f.thr_force.lo, rz), f.thr_force.hi = keep(f.thr_force.hi, rz);
-  f.thr_acc.lo = keep(f.thr_acc.lo, rz);
+  f.thr_acc.lo = keep(f.thr_acc.lo, rz), f.thr_acc.hi = keep(f.thr_acc.hi, rz);
   f.thr_start.lo = keep(f.thr_start.lo, rz), f.thr_start.hi = keep(f.thr_start.hi, rz);
   f.usable = !m.bad() && c.unit_mass;
   return f;
@@ -68,24 +77,39 @@ template <bool STATIC_VEL>
 __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, const SmemObstacles &obs,
                                           const uint16_t *cand, double *fbuf, const KnownBits &known, int type,
                                           const AgentConsts &c, const FastConsts &fc, v3 init_pos,
-                                          const double *rot_row, v3 goal_vec, const Prologue &pr, v3 &p, v3 &v,
-                                          double &min_obs) {
+                                          double *rot_row, const double *random_row, v3 goal_vec, const Prologue &pr,
+                                          v3 &p, v3 &v, double &min_obs, unsigned *why = nullptr) {
+  // why (developer statistics, PMAF_FAST_STATS builds): bit mask of the reasons a step was not taken
+#define PMAF_RARE(bit, cond)                   \
+  do {                                         \
+    const bool c_ = (cond);                    \
+    rare |= c_;                                \
+    if (why) *why |= c_ ? (1u << (bit)) : 0u;  \
+  } while (0)
   const StepNorms &sn = pr.sn;
   const int n_cand = pr.n_cand;
-  if (!fc.usable | (n_cand < 0) | (n_cand > 32)) return false;
+  if (!fc.usable | (n_cand < 0) | (n_cand > 32)) {
+    if (why) *why |= 1u;
+    return false;
+  }
   bool rare = false;
   // gate (:315-317)
   const v3 d0 = sub3(p, init_pos);
   const double z0 = dot3(d0, d0);
   const bool near_start = z0 < fc.thr_start.lo;
-  rare |= !near_start & !(z0 > fc.thr_start.hi);
+  PMAF_RARE(1, !near_start & !(z0 > fc.thr_start.hi));
   const bool gate_open = !(sn.dist_goal < c.approach_dist) & !((sn.vn < c.half_vmax) & near_start);
+  // repelForce (:159-181): the sentinel must be out of its shell, then its term is +0
+  const v3 dvs = sub3(p, obs.pos(P.n_obs - 1));
+  PMAF_RARE(6, !(dot3(dvs, dvs) > c.repel_far2));
   // attractorForceScaling's early exit (:215-218) depends on the agent only
   const bool kgs_zero = (dot3(goal_vec, v) <= 0.0) & (sn.vn < c.vmax90) & (sn.dist_goal > 0.15);
 
   v3 force = mk3(0.0, 0.0, 0.0);
   double min_d = (double)INFINITY, kgs_closest = 1.0;
-  bool has_closest = false;
+  bool has_closest = false, latch = false, latch_mine = false;
+  int latch_i = 0;
+  v3 latch_rot = force;
   if (gate_open & (n_cand > 0)) {
     g.sync();  // cand[] was written by the prologue's broad phase
     // ---- narrow phase: one lane per candidate, idle lanes shadow candidate 0 ----
@@ -94,8 +118,8 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     const v3 oi = obs.pos(i);
     const double rs = obs.rsum(i);
     const bool is_known = known.test(i);
-    const bool uses_rot = (type != GOAL_HEURISTIC) & (type != VEL_HEURISTIC);
-    v3 rot_i = mk3(0.0, 0.0, 1.0);
+    const bool uses_rot = (fc.tbits & kTUsesRot) != 0;
+    v3 rot_i = mk3(0.0, 0.0, 1.0);  // GOAL :408-412, VEL :539-543; default of a skipped unknown obstacle
     if (uses_rot & is_known) rot_i = ld3(rot_row + 3 * i);
     const v3 rov = sub3(oi, p);
     const v3 rel = STATIC_VEL ? v : sub3(v, obs.vel(i));
@@ -109,7 +133,28 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     const bool counts = active & !skip;             // :86-88
     const bool close = active & (d < c.shell);      // closest-obstacle search ignores the skip test (:201-211)
     const bool in_shell = close & !skip;            // :91
-    const bool first_seen = in_shell & !is_known;   // :92-96 -> general step
+    const bool first_seen = in_shell & !is_known;   // :92-96
+    // first detection latches the rotation vector (calculateRotationVector, :408-611). RANDOM :559-566 is one
+    // cross product with the unit goal vector the prologue already holds (bit-identical to rot_random);
+    // GOAL / VEL latch (0,0,1); HAD and the two obstacle heuristics (three agents of a population) take a
+    // cold, group-uniform branch: cooperative nearest-neighbour scans (:434-446), then the out-of-line
+    // IEEE evaluation, exactly as the general step does (eval_candidate).
+    if (first_seen & ((fc.tbits & kTRandom) != 0)) rot_i = cross3(pr.ghat, ld3(random_row + 3 * i));
+    if ((fc.tbits & (kTUsesRot | kTRandom)) == kTUsesRot) {
+      unsigned todo = g.ballot(first_seen);
+      if (__builtin_expect(todo != 0u, 0)) {
+        int nn = 0;
+        if (fc.tbits & kTNeedsNN) {
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int found = nearest_other_obstacle(g, obs, P.n_obs - 1, g.bcast(i, src));
+            if (g.lane == src) nn = found;
+          }
+        }
+        if (first_seen) rot_i = first_rotation_vector(type, p, P.goal, to_obs, oi, obs.pos(nn), random_row + 3 * i);
+      }
+    }
     // attractorForceScaling's tail for THIS obstacle (:219-226), used if it turns out to be the closest
     const double sd = fb.sqrt_(d);
     const double w1 = 1 - exp_main(fb, fb.quot_(-sd, c.shell, fc.y_shell));
@@ -129,15 +174,19 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     }
     const v3 nv_eigen = zr > 0.0 ? nv : rel;
     v3 cin = cross3(to_obs, rot_i);
-    if (type == GOAL_HEURISTIC) cin = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
-    if (type == VEL_HEURISTIC) cin = sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs)));
+    if (fc.tbits & kTGoal) cin = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+    if (fc.tbits & kTVel) cin = sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs)));
     double nc, yc;
     fb.sqrt_rcp_(dot3(cin, cin), nc, yc);
     v3 current = fb.quot3_(cin, nc, yc);
     if (!uses_rot & (nc < 1e-10)) current = mk3(0.0, 0.0, 1.0);
     const v3 f = mul3(cross3(nv, cross3(current, nv)), fb.div_(c.k_circ, d * d));
     const bool contributes = in_shell & (vel_norm != 0);
-    const bool lane_rare = active & (fa.bad() | first_seen | (close & fb.bad()));
+    const bool lane_rare = active & (fa.bad() | (close & fb.bad()));
+    if (why) {
+      if (g.ballot(active & fa.bad())) *why |= 1u << 2;
+      if (g.ballot(active & close & fb.bad())) *why |= 1u << 4;
+    }
 
     // ---- force_ += curr_force in obstacle order (:106): staged by rank, zero-padded, summed front to back ----
     const unsigned lt_mask = (1u << g.lane) - 1u;
@@ -152,6 +201,8 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     has_closest = who != 0u;
     kgs_closest = g.bcast(kgs, (__ffs(who) - 1) & 31);
     rare |= g.ballot(lane_rare) != 0u;
+    latch = g.ballot(first_seen) != 0u;
+    latch_mine = first_seen, latch_i = i, latch_rot = rot_i;
     g.sync();
 #pragma unroll
     for (int j = 0; j < kFastSumUnroll; ++j) force = add3(force, ld3(fbuf + 3 * j));
@@ -166,17 +217,25 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
   const double new_min_obs = min_d < min_obs ? min_d : min_obs;
   const double fz = dot3(force, force);
   const bool big = fz > fc.thr_force.hi;  // |F| > 1e-5 (:319)
-  rare |= !big & !(fz < fc.thr_force.lo);
+  PMAF_RARE(5, !big & !(fz < fc.thr_force.lo));
   const double k_goal_scale = (has_closest & big) ? kgs_closest : 1.0;
-  // repelForce (:159-181): the sentinel must be out of its shell, then the term is +0
-  const v3 dvs = sub3(p, obs.pos(P.n_obs - 1));
-  rare |= !(dot3(dvs, dvs) > c.repel_far2);
-  force = add3(force, mk3(0.0, 0.0, 0.0));
+  force = add3(force, mk3(0.0, 0.0, 0.0));  // += total_repel_force (:179), zero here
   // attractorForce (:183-193)
   const v3 fa3 = add3(force, mul3(sub3(sn.vel_des, v), k_goal_scale * c.k_damp));
   if (c.k_attr != 0.0) force = fa3;
-  // updatePositionAndVelocity (:253-268), unit mass, no acceleration clamp
-  rare |= !(dot3(force, force) < fc.thr_acc.lo);
+  // updatePositionAndVelocity (:253-268), unit mass; the acceleration clamp (|a| > 13) is a uniform branch
+  {
+    const double zacc = dot3(force, force);
+    const bool clamp = zacc > fc.thr_acc.hi;
+    PMAF_RARE(7, !clamp & !(zacc < fc.thr_acc.lo));
+    if (clamp) {
+      FastMath fc2;
+      double na, ya;
+      fc2.sqrt_rcp_(zacc, na, ya);
+      force = mul3(force, fc2.quot_(13.0, na, ya));
+      PMAF_RARE(8, fc2.bad());
+    }
+  }
   const double dt = P.pred_dt;
   const v3 np = mk3((p.x + 0.5 * force.x * dt * dt) + v.x * dt, (p.y + 0.5 * force.y * dt * dt) + v.y * dt,
                     (p.z + 0.5 * force.z * dt * dt) + v.z * dt);
@@ -186,10 +245,18 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
   fm.sqrt_rcp_(dot3(nvel, nvel), vel_norm, yvn);
   const double scale = fm.quot_(c.vel_max, vel_norm, yvn);
   if (vel_norm > c.vel_max) nvel = mul3(nvel, scale);
-  rare |= fm.bad();
+  PMAF_RARE(8, fm.bad());
   if (__builtin_expect(rare, 0)) return false;
+  if (__builtin_expect(latch, 0)) {  // commit the first detections of this step (:93-95)
+    if (latch_mine) {
+      st3(rot_row + 3 * latch_i, latch_rot);
+      known.set(latch_i);
+    }
+    g.sync();
+  }
   p = np, v = nvel, min_obs = new_min_obs;
   return true;
+#undef PMAF_RARE
 }
 #endif  // __CUDACC__
 

@@ -449,9 +449,13 @@ PMAF_HDT void field_pass(const G &g, const Obs &obs, int n_field, const uint16_t
     FastMath fm;
     CandEval r = eval_candidate<STATIC_VEL, SPEC>(fm, g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal,
                                             ghat, c, known, rot_row, random_row);
-    if (__builtin_expect(g.ballot(fm.bad()) != 0u, 0))
-      r = eval_candidate_exact<STATIC_VEL, SPEC>(g, obs, n_field, active, i, type, p, v, goal_vec, sn, nv_static, goal, ghat,
-                                           c, known, rot_row, random_row);
+    if (__builtin_expect(g.ballot(fm.bad()) != 0u, 0)) {
+      // the out-of-line call takes the norms by reference: hand it a copy made on this cold path, so that
+      // the caller's prologue values stay in registers instead of being written to the stack every step
+      const StepNorms sn_copy = sn;
+      r = eval_candidate_exact<STATIC_VEL, SPEC>(g, obs, n_field, active, i, type, p, v, goal_vec, sn_copy, nv_static, goal,
+                                                 ghat, c, known, rot_row, random_row);
+    }
     PMAF_T(3);
     // ---- commit ----
     if (r.d < lcd) lcd = r.d, lci = i, lkgs = r.kgs;  // the search ignores the skip test (:201-211)

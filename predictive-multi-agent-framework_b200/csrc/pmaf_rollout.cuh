@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   // latency build, one warp per agent: common steps take the straight-line path (pmaf_fast.cuh)
   constexpr bool FAST = OCC == 1 && LPA == 32;
   FastConsts fc;
-  if (FAST) fc = make_fast_consts(k, rz);
+  if (FAST) fc = make_fast_consts(k, type, rz);
   const unsigned long long t0 = global_timer_ns();
   int steps_run = 0, general_steps = 0;
   bool alive = have_agent;
@@ -279,11 +279,26 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
       if (sn.dist_goal > 0.1 && n_path < max_steps) {  // :310-311
         const v3 prev = p;
         bool done = false;
+#if defined(PMAF_FAST_STATS)
+        unsigned why_bits = 0u;
+        unsigned *why = &why_bits;
+#else
+        unsigned *why = nullptr;
+#endif
         if constexpr (FAST)
-          done = fast_step<!DYNAMIC>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, goal_vec, pr, p, v,
-                                     min_obs);
+          done = fast_step<!DYNAMIC>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec,
+                                     pr, p, v, min_obs, why);
         if (!done) {
           ++general_steps;
+#if defined(PMAF_EXPERIMENT_NO_GENERAL)
+        }
+        if (false) {
+#endif
+#if defined(PMAF_FAST_STATS)
+          if (g.gl == 0)
+            for (int b = 0; b < 12; ++b)
+              if (why_bits >> b & 1u) atomicAdd(P.step_counter + 4 + b, 1ull);
+#endif
           agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row,
                                          goal_vec, pr, p, v, min_obs PMAF_T_PASS);
         }

@@ -18,7 +18,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmaf.so")
+# PMAF_LIB: developer override to load an instrumented variant of the library (tools/*.py)
+LIB_PATH = os.path.join(_HERE, os.environ.get("PMAF_LIB", "libpmaf.so"))
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -48,7 +49,7 @@ API_SYMBOLS = [
     "pmaf_get_initial_position", "pmaf_get_dist_from_goal", "pmaf_get_best_agent_type", "pmaf_get_best_agent_id",
     "pmaf_get_num_prediction_steps", "pmaf_get_real_num_prediction_steps", "pmaf_get_agent_summaries",
     "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
-    "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters",
+    "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters", "pmaf_get_fast_stats",
     "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
     "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles", "pmaf_get_best_paths",
 ]
@@ -338,6 +339,15 @@ class CfManager:
         c = Counters()
         self._check(self.lib.pmaf_get_counters(self.h, C.byref(c)))
         return {f[0]: getattr(c, f[0]) for f in Counters._fields_}
+
+    def fast_stats(self):
+        """Reasons that kept steps off the straight-line step (PMAF_FAST_STATS builds; zeros otherwise)."""
+        self.counters()
+        out = (C.c_uint64 * 12)()
+        self._check(self.lib.pmaf_get_fast_stats(self.h, out))
+        names = ["unusable_or_candidates", "start_threshold", "range_distance_chain", "first_detection_general",
+                 "range_force_chain", "force_threshold", "sentinel_in_reach", "acceleration_clamp", "range_integrator"]
+        return {n: int(out[i]) for i, n in enumerate(names)}
 
     def set_upload_dedup(self, dedup):
         self._check(self.lib.pmaf_set_upload_dedup(self.h, 1 if dedup else 0))
