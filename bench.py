@@ -9,7 +9,8 @@ integration steps (agents x (horizon-1) on the synthetic workloads) per second.
   value   device-resident: pmaf_tick (one fused chain per tick), obstacles already in HBM,
           timed with CUDA events on the planner's stream (pmaf_timer_*), L2 flushed between ticks.
   e2e     the five reference-facing CfManager calls per tick through the C ABI with HOST buffers
-          (obstacle lists re-uploaded every call, results read back), wall clock.
+          (obstacle lists re-uploaded every call, results read back), driven by the library's C++
+          host loop pmaf_dry_run (the reference's caller is a C++ node), wall clock.
   --impl reference   the reference's own CPU implementation (oracle/_ref when built, else the
           C port) on all host threads, same workload and metric.
 """
@@ -210,18 +211,17 @@ def run_ours(args, rank, world, local_rank):
     rollout_ms = (c1["rollout_ms_total"] - c0["rollout_ms_total"]) / args.steps
 
     # ---- e2e: the reference-facing calls with host buffers, wall clock ----
+    # the library's C++ host loop (pmaf_dry_run: planCallback's five CfManager calls per tick through the C ABI,
+    # obstacle lists in host memory, uploaded by every call that takes them); L2 flushed before each tick and
+    # the tick's rollout awaited inside its timed region
     mgr.set_upload_dedup(False)
+    mgr.stop_prediction()
     e0 = mgr.counters()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        mgr.flush_l2()
-        mgr.stop_prediction()
-        barrier()
-        t0 = time.perf_counter()
-        loop.control_tick(mgr, sc, feed)
-        mgr.stop_prediction()
-        e2e_s += time.perf_counter() - t0
-        feed.step()
+    barrier()
+    n_feed = sc.num_obstacles - 1 if feed.active else 0
+    e2e_s, _, _, _ = mgr.dry_run(args.steps, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
+                                 sc.k_path_len, sc.k_safe_dist, sc.k_workspace, sc.ws_limits,
+                                 feed_frequency=feed.frequency, wait_rollout=True, flush_l2=True)
     e1 = mgr.counters()
     e2e_steps_local = e1["agent_steps_total"] - e0["agent_steps_total"]
 
@@ -254,7 +254,8 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) / args.steps,
                     "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) / args.steps,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "stop_prediction, evaluate_agents, move_real_agent, reset_agents, start_prediction"},
+                    "api": "pmaf_dry_run (C++ host loop): per tick stop_prediction, evaluate_agents, move_real_agent, "
+                           "get_next_position/velocity, reset_agents, start_prediction on host obstacle lists"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": measured_traffic(args.workload) if world == 1 else None,

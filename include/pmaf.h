@@ -196,6 +196,25 @@ int pmaf_get_best_paths(pmaf_planner *p, int k, int stride, int max_points, int 
 /* costs computed by the last evaluate_agents */
 int pmaf_get_costs(pmaf_planner *p, double *costs /* [n_agents] */);
 
+/* ---- dry-run relay ------------------------------------------------------------------------------------ */
+/* The in-process equivalent of launch/dry_run.launch (:9,41 relays the planner's `goals` output back as
+ * its `position` input): runs `ticks` control ticks — planCallback, panda_bimanual_control.cpp:329-369:
+ * stop_prediction, evaluate_agents, move_real_agent, get_next_position/velocity, reset_agents,
+ * start_prediction — through the entry points above with the caller's HOST obstacle lists. After every
+ * tick the obstacle feed of dynamic_obstacle_node (dynamic_obstacle_node.cpp:352-369) advances
+ * obs_pos[0 .. n_feed) in place by obs_vel / feed_frequency (n_feed = 0: static scene; the node feeds
+ * every obstacle but the trailing sentinel). Optional outputs per tick: best[ticks], next_pos[ticks][3],
+ * next_vel[ticks][3]. *seconds = wall time spent inside the ticks (CLOCK_MONOTONIC around each tick).
+ * flags: PMAF_DRY_RUN_WAIT_ROLLOUT waits for each tick's rollout inside its timed region (benchmarks: a
+ * tick then costs calls + rollout); PMAF_DRY_RUN_FLUSH_L2 evicts the L2 before each tick, untimed. */
+#define PMAF_DRY_RUN_WAIT_ROLLOUT 1
+#define PMAF_DRY_RUN_FLUSH_L2 2
+int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_pos, const double *obs_vel, const double *obs_rad,
+                 int n_feed, double feed_frequency, double delta_t, double k_goal_dist, double k_path_len,
+                 double k_safe_dist, double k_workspace, const double ws_limits[6], int flags, double *seconds,
+                 int *best /* [ticks] or NULL */, double *next_pos /* [ticks][3] or NULL */,
+                 double *next_vel /* [ticks][3] or NULL */);
+
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 typedef struct {
   uint64_t kernel_launches;  /* kernels of this library launched on the handle since create */

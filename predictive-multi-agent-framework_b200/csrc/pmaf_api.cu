@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstddef>
 #include <cstring>
+#include <ctime>
 #include <random>
 #include <string>
 #include <vector>
@@ -52,27 +54,34 @@ template <class T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool owned = true;
   cudaError_t resize(size_t count) {
     if (count == n && p) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr, n = 0;
+    if (p && owned) cudaFree(p);
+    p = nullptr, n = 0, owned = true;
     if (count == 0) return cudaSuccess;
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
     if (e == cudaSuccess) n = count;
     return e;
   }
+  void alias(T *ptr, size_t count) {  // a view into another allocation
+    release();
+    p = ptr, n = count, owned = false;
+  }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr, n = 0;
+    if (p && owned) cudaFree(p);
+    p = nullptr, n = 0, owned = true;
   }
 };
 
-struct HostOut {  // pinned D2H landing zone
+// Everything a tick reads back lives in ONE device block with the layout of its pinned host mirror, so
+// that each call's results come back in a single small copy (eval + best; real + its path; all three).
+struct HostOut {
   EvalResult eval;
   DeviceBest best;
   RealState real;
-  unsigned long long steps[16];
   double real_path[256 * 3];
+  unsigned long long steps[16];
 };
 
 struct pmaf_planner {
@@ -108,6 +117,7 @@ struct pmaf_planner {
   DevBuf<unsigned char> rec_all;   // all-gathered records [world]
   bool nccl_owned = false;
   DevBuf<unsigned long long> step_counter;
+  DevBuf<HostOut> d_out;  // eval, best, real, real_path_out, step_counter are views into it
   DevBuf<unsigned char> l2_scratch;
   DevBuf<long long> section_cycles;
   DevBuf<unsigned> runtime_zero;
@@ -357,11 +367,10 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(cudaEventCreate(&p->ev_t1));
   CU(cudaMallocHost(&p->h_out, sizeof(HostOut)));
   memset(p->h_out, 0, sizeof(HostOut));
-  CU(p->best.resize(1));
-  CU(p->eval.resize(1));
+  CU(p->d_out.resize(1));
+  p->eval.alias(&p->d_out.p->eval, 1), p->best.alias(&p->d_out.p->best, 1), p->real.alias(&p->d_out.p->real, 1);
+  p->real_path_out.alias(p->d_out.p->real_path, 256 * 3), p->step_counter.alias(p->d_out.p->steps, 16);
   CU(p->rec.resize(argmin_record_bytes(0)));
-  CU(p->real.resize(1));
-  CU(p->step_counter.resize(16));
   CU(p->scratch.resize(16));
   CU(p->runtime_zero.resize(1));
   CU(cudaMemsetAsync(p->runtime_zero.p, 0, sizeof(unsigned), p->stream));
@@ -393,6 +402,7 @@ extern "C" int pmaf_destroy(pmaf_planner *p) {
   p->n_path.release(), p->reached.release(), p->known.release(), p->image.release(), p->real_known.release();
   p->real.release(), p->best.release(), p->eval.release(), p->rec.release(), p->step_counter.release();
   p->rec_all.release();
+  p->d_out.release();
   nccl_release(p);
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -518,12 +528,10 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
   CU(p->obs_pos.resize(O * 3));
   CU(p->obs_vel.resize(O * 3));
   CU(p->obs_rad.resize(O));
-  CU(p->live_pos.resize(O * 3));
-  CU(p->live_vel.resize(O * 3));
-  CU(p->live_rad.resize(O));
+  CU(p->live_pos.resize(O * 7));  // pos | vel | rad in one block: one upload per call
+  p->live_vel.alias(p->live_pos.p + 3 * O, 3 * O), p->live_rad.alias(p->live_pos.p + 6 * O, O);
   CU(p->real_known.resize(O));
   CU(p->real_rot.resize(O * 3));
-  CU(p->real_path_out.resize(256 * 3));
   CU(p->rec.resize(argmin_record_bytes((int)O)));
   CU(p->rec_all.resize(argmin_record_bytes((int)O) * (size_t)p->world));
   {  // best_agent_ survives init (quirk 6); keep the overlapping part of its random vectors
@@ -810,8 +818,10 @@ extern "C" int pmaf_evaluate_agents(pmaf_planner *p, int n_obs, const double *ob
   if (int rc = finish_rollout(p)) return rc;
   const CostParams C = make_cost(k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits);
   if (int rc = launch_evaluate(p, C)) return rc;
-  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult))) return rc;
-  if (int rc = d2h(p, &p->h_out->best, p->best.p, sizeof(DeviceBest))) return rc;
+  static_assert(offsetof(HostOut, best) == sizeof(EvalResult) && offsetof(HostOut, real) == sizeof(EvalResult) + sizeof(DeviceBest) &&
+                    offsetof(HostOut, real_path) == offsetof(HostOut, real) + sizeof(RealState),
+                "HostOut members must be contiguous");
+  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
   CU(cudaStreamSynchronize(p->stream));
   p->h_eval = p->h_out->eval, p->h_best = p->h_out->best;
   *best_index = p->h_eval.best_index;
@@ -833,9 +843,13 @@ static int upload_live(pmaf_planner *p, int n_obs, const double *obs_pos, const 
   memcpy(last.data() + 6 * n, obs_rad, n * sizeof(double));
   if (int rc = stage_acquire(p, 7 * n)) return rc;
   memcpy(p->h_stage, last.data(), 7 * n * sizeof(double));
-  if (int rc = h2d(p, p->live_pos.p, p->h_stage, 3 * n * sizeof(double))) return rc;
-  if (int rc = h2d(p, p->live_vel.p, p->h_stage + 3 * n, 3 * n * sizeof(double))) return rc;
-  if (int rc = h2d(p, p->live_rad.p, p->h_stage + 6 * n, n * sizeof(double))) return rc;
+  if (n_obs == p->O) {  // the usual case: the device block has the staging layout, one copy
+    if (int rc = h2d(p, p->live_pos.p, p->h_stage, 7 * n * sizeof(double))) return rc;
+  } else {
+    if (int rc = h2d(p, p->live_pos.p, p->h_stage, 3 * n * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->live_vel.p, p->h_stage + 3 * n, 3 * n * sizeof(double))) return rc;
+    if (int rc = h2d(p, p->live_rad.p, p->h_stage + 6 * n, n * sizeof(double))) return rc;
+  }
   return stage_release(p);
 }
 
@@ -867,8 +881,7 @@ extern "C" int pmaf_move_real_agent(pmaf_planner *p, int n_obs, const double *ob
   for (int done = 0; done < steps;) {
     const int chunk = std::min(steps - done, 256);
     if (int rc = launch_real(p, n_obs, delta_t, chunk, agent_id)) return rc;
-    if (int rc = d2h(p, &p->h_out->real, p->real.p, sizeof(RealState))) return rc;
-    if (int rc = d2h(p, p->h_out->real_path, p->real_path_out.p, (size_t)chunk * 3 * sizeof(double))) return rc;
+    if (int rc = d2h(p, &p->h_out->real, p->real.p, sizeof(RealState) + (size_t)chunk * 3 * sizeof(double))) return rc;
     CU(cudaStreamSynchronize(p->stream));
     p->h_real = p->h_out->real;
     p->real_path.insert(p->real_path.end(), p->h_out->real_path, p->h_out->real_path + (size_t)chunk * 3);
@@ -899,13 +912,18 @@ extern "C" int pmaf_reset_agents(pmaf_planner *p, const double pos[3], const dou
   if (int rc = finish_rollout(p)) return rc;
   if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
   if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, pos)) return rc;
-  if (int rc = stage_acquire(p, 6)) return rc;
-  memcpy(p->h_stage, pos, 3 * sizeof(double));
-  memcpy(p->h_stage + 3, vel, 3 * sizeof(double));
-  if (int rc = h2d(p, p->scratch.p, p->h_stage, 6 * sizeof(double))) return rc;
-  if (int rc = stage_release(p)) return rc;
+  // the node passes getNextPosition() / getNextVelocity() (node:350): those are the real agent's state, which
+  // the device already holds bit for bit — no upload then
+  const bool from_real = memcmp(pos, p->h_real.pos, 3 * sizeof(double)) == 0 && memcmp(vel, p->h_real.vel, 3 * sizeof(double)) == 0;
+  if (!from_real) {
+    if (int rc = stage_acquire(p, 6)) return rc;
+    memcpy(p->h_stage, pos, 3 * sizeof(double));
+    memcpy(p->h_stage + 3, vel, 3 * sizeof(double));
+    if (int rc = h2d(p, p->scratch.p, p->h_stage, 6 * sizeof(double))) return rc;
+    if (int rc = stage_release(p)) return rc;
+  }
   p->fused_valid = p->have_cost;
-  if (int rc = launch_reset(p, true, false, p->scratch.p, n_obs, p->live_pos.p, p->live_vel.p, true, true))
+  if (int rc = launch_reset(p, true, from_real, p->scratch.p, n_obs, p->live_pos.p, p->live_vel.p, true, true))
     return rc;
   p->obstacles_advanced = false;
   p->agents_touched = true;
@@ -932,9 +950,7 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, p->h_real.pos)) return rc;
   p->fused_valid = true;
   if (int rc = launch_reset(p, true, true, nullptr, n_obs, p->live_pos.p, p->live_vel.p, true, true)) return rc;
-  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult))) return rc;
-  if (int rc = d2h(p, &p->h_out->best, p->best.p, sizeof(DeviceBest))) return rc;
-  if (int rc = d2h(p, &p->h_out->real, p->real.p, sizeof(RealState))) return rc;
+  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest) + sizeof(RealState))) return rc;
   CU(cudaEventRecord(p->ev_d2h, p->stream));
   p->obstacles_advanced = false;
   if (int rc = launch_rollout(p)) return rc;
@@ -946,6 +962,55 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
     if (next_pos) next_pos[i] = p->h_real.pos[i];
     if (next_vel) next_vel[i] = p->h_real.vel[i];
   }
+  return 0;
+}
+
+// The in-process equivalent of launch/dry_run.launch (:9,41: the planner's `goals` output relayed back as its
+// `position` input) in the reference's language: `ticks` planCallbacks (node:329-369) through the public
+// entry points above, in the node's order, with HOST obstacle lists; between ticks the obstacle feed of
+// dynamic_obstacle_node (:352-369) advances obstacles [0, n_feed) by vel / feed_frequency.
+extern "C" int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_pos, const double *obs_vel,
+                            const double *obs_rad, int n_feed, double feed_frequency, double delta_t, double k_goal_dist,
+                            double k_path_len, double k_safe_dist, double k_workspace, const double ws_limits[6],
+                            int flags, double *seconds, int *best, double *next_pos, double *next_vel) {
+  ENTER(p);
+  NEED_INIT(p);
+  REQUIRE(ticks >= 0 && obs_pos && obs_vel && obs_rad && ws_limits && n_feed >= 0 && n_feed <= n_obs, PMAF_ERR_ARG,
+          "pmaf_dry_run: bad argument");
+  double total = 0.0;
+  for (int t = 0; t < ticks; ++t) {
+    if (flags & PMAF_DRY_RUN_FLUSH_L2) {
+      if (int rc = pmaf_flush_l2(p)) return rc;
+    }
+    if (flags & (PMAF_DRY_RUN_FLUSH_L2 | PMAF_DRY_RUN_WAIT_ROLLOUT)) {  // drain before the clock starts
+      if (int rc = pmaf_stop_prediction(p)) return rc;
+    }
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    int b = 0;
+    double pos[3], vel[3];
+    if (int rc = pmaf_stop_prediction(p)) return rc;
+    if (int rc = pmaf_evaluate_agents(p, n_obs, obs_pos, obs_vel, obs_rad, k_goal_dist, k_path_len, k_safe_dist, k_workspace,
+                                      ws_limits, &b))
+      return rc;
+    if (int rc = pmaf_move_real_agent(p, n_obs, obs_pos, obs_vel, obs_rad, delta_t, 1, b)) return rc;
+    if (int rc = pmaf_get_next_position(p, pos)) return rc;
+    if (int rc = pmaf_get_next_velocity(p, vel)) return rc;
+    if (int rc = pmaf_reset_agents(p, pos, vel, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+    if (int rc = pmaf_start_prediction(p)) return rc;
+    if (flags & PMAF_DRY_RUN_WAIT_ROLLOUT) {
+      if (int rc = pmaf_stop_prediction(p)) return rc;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    total += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    if (best) best[t] = b;
+    for (int i = 0; i < 3; ++i) {
+      if (next_pos) next_pos[3 * t + i] = pos[i];
+      if (next_vel) next_vel[3 * t + i] = vel[i];
+    }
+    for (int i = 0; i < 3 * n_feed; ++i) obs_pos[i] += obs_vel[i] / feed_frequency;
+  }
+  if (seconds) *seconds = total;
   return 0;
 }
 

@@ -49,7 +49,7 @@ API_SYMBOLS = [
     "pmaf_get_initial_position", "pmaf_get_dist_from_goal", "pmaf_get_best_agent_type", "pmaf_get_best_agent_id",
     "pmaf_get_num_prediction_steps", "pmaf_get_real_num_prediction_steps", "pmaf_get_agent_summaries",
     "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
-    "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters", "pmaf_get_fast_stats",
+    "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters", "pmaf_get_fast_stats", "pmaf_dry_run",
     "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
     "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles", "pmaf_get_best_paths",
 ]
@@ -118,6 +118,9 @@ def load_library():
     lib.pmaf_get_costs.argtypes = [H, _dp]
     lib.pmaf_get_best_paths.argtypes = [H, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp]
     lib.pmaf_get_counters.argtypes = [H, C.POINTER(Counters)]
+    lib.pmaf_get_fast_stats.argtypes = [H, C.POINTER(C.c_uint64)]
+    lib.pmaf_dry_run.argtypes = [H, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, _ip, _dp, _dp]
     lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int, C.c_int]
     lib.pmaf_set_upload_dedup.argtypes = [H, C.c_int]
     lib.pmaf_timer_start.argtypes = [H]
@@ -250,6 +253,22 @@ class CfManager:
                                        float(k_goal_dist), float(k_path_len), float(k_safe_dist), float(k_workspace),
                                        _d(_f64(ws_limits, (6,))), C.byref(best), _d(p), _d(v)))
         return best.value, p, v
+
+    def dry_run(self, ticks, obs_pos, obs_vel, obs_rad, n_feed, delta_t, k_goal_dist, k_path_len, k_safe_dist,
+                k_workspace, ws_limits, feed_frequency=100.0, wait_rollout=False, flush_l2=False):
+        """`ticks` planCallbacks in the library's C++ host loop (pmaf_dry_run) on HOST obstacle arrays; obs_pos is
+        advanced in place by the obstacle feed. Returns (seconds inside the ticks, best[ticks], next_pos, next_vel)."""
+        assert obs_pos.dtype == np.float64 and obs_pos.flags["C_CONTIGUOUS"]
+        ov, orad = _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        best = np.zeros(max(ticks, 1), dtype=np.int32)
+        npos, nvel = np.zeros((max(ticks, 1), 3)), np.zeros((max(ticks, 1), 3))
+        sec = C.c_double()
+        flags = (1 if wait_rollout else 0) | (2 if flush_l2 else 0)
+        self._check(self.lib.pmaf_dry_run(self.h, int(ticks), len(orad), _d(obs_pos), _d(ov), _d(orad), int(n_feed),
+                                          float(feed_frequency), float(delta_t), float(k_goal_dist), float(k_path_len),
+                                          float(k_safe_dist), float(k_workspace), _d(_f64(ws_limits, (6,))), flags,
+                                          C.byref(sec), _i(best), _d(npos), _d(nvel)))
+        return sec.value, best[:ticks], npos[:ticks], nvel[:ticks]
 
     # ---- getters ----------------------------------------------------------------------------------
     def _vec3(self, fn):

@@ -107,6 +107,30 @@ def test_fused_tick_equals_call_by_call(name):
     assert_bit_identical(got, a, keys=list(got), ctx=f"{name}: ")
 
 
+@pytest.mark.parametrize("name", ["anchor_A10_H1500", "moving0", "moving2_freq2", "near326_switching", "task_sim_kobo_dyn_spheres1"])
+def test_cpp_dry_run_loop_matches_reference_golden(name):
+    """pmaf_dry_run (the library's C++ host loop: planCallback order on host obstacle lists, obstacle feed
+    between ticks) reproduces the reference build's golden tick records bit for bit, with and without
+    waiting for each tick's rollout."""
+    sc = CASES[name].scenario
+    want = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    ticks = len(want["best"])
+    for wait in (False, True):
+        p = _planner()
+        loop.plan_begin(p, sc)
+        feed = loop.ObstacleFeed(sc)
+        n_feed = sc.num_obstacles - 1 if feed.active else 0
+        sec, best, pos, vel = p.dry_run(ticks, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
+                                        sc.k_path_len, sc.k_safe_dist, sc.k_workspace, sc.ws_limits,
+                                        feed_frequency=feed.frequency, wait_rollout=wait, flush_l2=wait)
+        p.stop_prediction()
+        got = dict(best=best, next_pos=pos, next_vel=vel, steps=p.get_agent_summaries()["steps"])
+        ref = dict(best=want["best"], next_pos=want["next_pos"], next_vel=want["next_vel"], steps=want["steps"][-1])
+        assert_bit_identical(got, ref, keys=list(got), ctx=f"{name} wait={wait}: ")
+        assert sec > 0
+        p.close()
+
+
 def _oracle():
     from oracle import cpu_planners
 
