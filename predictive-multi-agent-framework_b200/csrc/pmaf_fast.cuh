@@ -88,17 +88,19 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
   } while (0)
   const StepNorms &sn = pr.sn;
   const int n_cand = pr.n_cand;
-  if (!fc.usable | (n_cand < 0) | (n_cand > 32)) {
-    if (why) *why |= 1u;
-    return false;
-  }
   bool rare = false;
   // gate (:315-317)
   const v3 d0 = sub3(p, init_pos);
   const double z0 = dot3(d0, d0);
   const bool near_start = z0 < fc.thr_start.lo;
-  PMAF_RARE(1, !near_start & !(z0 > fc.thr_start.hi));
+  const bool start_ambiguous = !near_start & !(z0 > fc.thr_start.hi);
   const bool gate_open = !(sn.dist_goal < c.approach_dist) & !((sn.vn < c.half_vmax) & near_start);
+  // ONE branch decides between this path and the general step: a closed gate (no field pass: the general
+  // step is as short), no or too many candidates, an unusable configuration
+  if (!(fc.usable & (n_cand > 0) & (n_cand <= 32) & gate_open & !start_ambiguous)) {
+    if (why) *why |= 1u;
+    return false;
+  }
   // repelForce (:159-181): the sentinel must be out of its shell, then its term is +0
   const v3 dvs = sub3(p, obs.pos(P.n_obs - 1));
   PMAF_RARE(6, !(dot3(dvs, dvs) > c.repel_far2));
@@ -110,7 +112,7 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
   bool has_closest = false, latch = false, latch_mine = false;
   int latch_i = 0;
   v3 latch_rot = force;
-  if (gate_open & (n_cand > 0)) {
+  {
     g.sync();  // cand[] was written by the prologue's broad phase
     // ---- narrow phase: one lane per candidate, idle lanes shadow candidate 0 ----
     const bool active = g.gl < n_cand;
@@ -206,9 +208,13 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     g.sync();
 #pragma unroll
     for (int j = 0; j < kFastSumUnroll; ++j) force = add3(force, ld3(fbuf + 3 * j));
-    for (int j = kFastSumUnroll; j < n_contrib; j += 4) {
-      const v3 a0 = ld3(fbuf + 3 * j), a1 = ld3(fbuf + 3 * j + 3), a2 = ld3(fbuf + 3 * j + 6), a3 = ld3(fbuf + 3 * j + 9);
-      force = add3(add3(add3(add3(force, a0), a1), a2), a3);
+    if (n_contrib > kFastSumUnroll) {  // second block, zero-padded as well
+#pragma unroll
+      for (int j = kFastSumUnroll; j < 2 * kFastSumUnroll; ++j) force = add3(force, ld3(fbuf + 3 * j));
+      for (int j = 2 * kFastSumUnroll; j < n_contrib; j += 4) {
+        const v3 a0 = ld3(fbuf + 3 * j), a1 = ld3(fbuf + 3 * j + 3), a2 = ld3(fbuf + 3 * j + 6), a3 = ld3(fbuf + 3 * j + 9);
+        force = add3(add3(add3(add3(force, a0), a1), a2), a3);
+      }
     }
     g.sync();
   }

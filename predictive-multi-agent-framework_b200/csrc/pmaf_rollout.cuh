@@ -46,9 +46,11 @@ PMAF_HDT int broad_phase_unrolled(const G &g, const float4 *bp, int n_field, v3 
   for (int r = 0; r < ROUNDS; ++r) {
     const int i = r * LPA + g.gl;
     const bool in_range = i < n_field;
-    const float4 b = bp[in_range ? i : 0];
+    // unconditional load of a valid record (the image always holds n_field + 1 >= 1 of them): no branch
+    // around the shared-memory read, its latency overlaps the prologue's FP64 chains
+    const float4 b = bp[i < n_field ? i : n_field];
     const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
-    const bool cnd = in_range && dx * dx + dy * dy + dz * dz < b.w;
+    const bool cnd = in_range & (dx * dx + dy * dy + dz * dz < b.w);
     const unsigned m = g.ballot(cnd);
     if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
     n_cand += PMAF_POPC(m);
@@ -268,8 +270,9 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   double zseg = 1.0;  // |last path segment|^2: its square root joins the next step's prologue
   bool has_seg = false;
   PMAF_T_DECL;
+  if (DYNAMIC || alive)  // static scenes: an agent's warp leaves the loop directly when its rollout ends
   for (;;) {
-    if (alive) {
+    if (!DYNAMIC || alive) {
       const v3 goal_vec = sub3(goal, p);
       const Prologue pr = step_prologue<!DYNAMIC, OCC == 1>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zseg, has_seg, k);
       const StepNorms &sn = pr.sn;
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         ++steps_run;
         PMAF_T(7);
       } else {
+        if (!DYNAMIC) break;
         alive = false;
       }
     }
@@ -332,8 +336,6 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         bpw[i] = b;
       }
       __syncthreads();
-    } else if (!alive) {
-      break;
     }
   }
 
