@@ -374,7 +374,7 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(p->scratch.resize(16));
   CU(p->runtime_zero.resize(1));
   CU(cudaMemsetAsync(p->runtime_zero.p, 0, sizeof(unsigned), p->stream));
-#if defined(PMAF_SECTION_TIMERS)
+#if defined(PMAF_SECTION_TIMERS) || defined(PMAF_FAST_STATS)
   CU(p->section_cycles.resize(64 * 12));
   CU(cudaMemsetAsync(p->section_cycles.p, 0, 64 * 12 * sizeof(long long), p->stream));
 #endif

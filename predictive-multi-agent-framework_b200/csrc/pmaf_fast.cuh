@@ -142,19 +142,70 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     // cold, group-uniform branch: cooperative nearest-neighbour scans (:434-446), then the out-of-line
     // IEEE evaluation, exactly as the general step does (eval_candidate).
     if (first_seen & ((fc.tbits & kTRandom) != 0)) rot_i = cross3(pr.ghat, ld3(random_row + 3 * i));
+    bool latch_flag = false;
     if ((fc.tbits & (kTUsesRot | kTRandom)) == kTUsesRot) {
       unsigned todo = g.ballot(first_seen);
       if (__builtin_expect(todo != 0u, 0)) {
+#if defined(PMAF_FAST_STATS)
+        const long long tl0 = clock64();
+#endif
+        // cold (a few times per rollout of three agents), written inline with the branch-free arithmetic: an
+        // out-of-line call here costs more in register saves than the work itself
+        FastMath fscan, frot;
         int nn = 0;
-        if (fc.tbits & kTNeedsNN) {
+        if (fc.tbits & kTNeedsNN) {  // nearest other field obstacle, serial-scan semantics (:434-446)
+          const int n_field = P.n_obs - 1;
           while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const int found = nearest_other_obstacle(g, obs, P.n_obs - 1, g.bcast(i, src));
-            if (g.lane == src) nn = found;
+            const int id = g.bcast(i, src);
+            const v3 o_id = obs.pos(id);
+            double best = 100.0;
+            int best_i = 0x7fffffff;
+            for (int k = g.gl; k < n_field; k += 32) {
+              const v3 dk = sub3(o_id, obs.pos(k));
+              const double dist = fscan.sqrt_(k != id ? dot3(dk, dk) : 1.0);
+              if ((k != id) & (best > dist)) best = dist, best_i = k;
+            }
+            g.argmin_reduce_nonneg(best, best_i);
+            if (g.lane == src) nn = best_i == 0x7fffffff ? 0 : best_i;
           }
         }
-        if (first_seen) rot_i = first_rotation_vector(type, p, P.goal, to_obs, oi, obs.pos(nn), random_row + 3 * i);
+        v3 r;
+        if (type == HAD_HEURISTIC) {  // rot_had (:599-611)
+          const double sh = frot.div_(dot3(rov, goal_vec), sn.dist_goal * sn.dist_goal);
+          const v3 dh = sub3(add3(p, mul3(goal_vec, sh)), oi);
+          const v3 ch = cross3(dh, goal_vec);
+          double nh, yh;
+          frot.sqrt_rcp_(dot3(ch, ch), nh, yh);
+          r = frot.quot3_(ch, nh, yh);
+        } else {  // rot_obstacle (:447-460), rot_goal_obstacle (:493-517)
+          const v3 obstacle_vec = sub3(obs.pos(nn), oi);
+          const v3 obst_current = sub3(mul3(to_obs, dot3(obstacle_vec, to_obs)), obstacle_vec);
+          v3 cur = obst_current;
+          if (type == GOAL_OBSTACLE_HEURISTIC) {
+            const v3 goal_current = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+            double n1, y1, n2, y2, n3, y3;
+            frot.sqrt_rcp_(dot3(goal_current, goal_current), n1, y1);
+            frot.sqrt_rcp_(dot3(obst_current, obst_current), n2, y2);
+            cur = add3(frot.quot3_(goal_current, n1, y1), frot.quot3_(obst_current, n2, y2));
+            FastMath fsum;  // a sum below 1e-10 is replaced, whatever its square root did
+            fsum.sqrt_rcp_(dot3(cur, cur), n3, y3);
+            const v3 q3 = fsum.quot3_(cur, n3, y3);
+            const bool tiny = n3 < 1e-10;
+            frot.flag |= (fsum.bad() && !(dot3(cur, cur) == 0.0)) ? 1u : 0u;
+            cur = (tiny | (dot3(cur, cur) == 0.0)) ? mk3(0.0, 0.0, 1.0) : q3;
+          }
+          const v3 cr = cross3(cur, to_obs);
+          double nr, yr;
+          frot.sqrt_rcp_(dot3(cr, cr), nr, yr);
+          r = frot.quot3_(cr, nr, yr);
+        }
+        if (first_seen) rot_i = r;
+        latch_flag = fscan.bad() | (first_seen & frot.bad());
+#if defined(PMAF_FAST_STATS)
+        if (why) why[1] += (unsigned)(clock64() - tl0), why[2] += 1u;
+#endif
       }
     }
     // attractorForceScaling's tail for THIS obstacle (:219-226), used if it turns out to be the closest
@@ -184,7 +235,7 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     if (!uses_rot & (nc < 1e-10)) current = mk3(0.0, 0.0, 1.0);
     const v3 f = mul3(cross3(nv, cross3(current, nv)), fb.div_(c.k_circ, d * d));
     const bool contributes = in_shell & (vel_norm != 0);
-    const bool lane_rare = active & (fa.bad() | (close & fb.bad()));
+    const bool lane_rare = latch_flag | (active & (fa.bad() | (close & fb.bad())));
     if (why) {
       if (g.ballot(active & fa.bad())) *why |= 1u << 2;
       if (g.ballot(active & close & fb.bad())) *why |= 1u << 4;

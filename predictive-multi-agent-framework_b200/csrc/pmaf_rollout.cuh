@@ -270,6 +270,9 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   double zseg = 1.0;  // |last path segment|^2: its square root joins the next step's prologue
   bool has_seg = false;
   PMAF_T_DECL;
+#if defined(PMAF_FAST_STATS)
+  long long st_fast_cyc = 0, st_gen_cyc = 0, st_gen = 0, st_cand = 0, st_latch_cyc = 0, st_latch = 0;
+#endif
   if (DYNAMIC || alive)  // static scenes: an agent's warp leaves the loop directly when its rollout ends
   for (;;) {
     if (!DYNAMIC || alive) {
@@ -283,10 +286,15 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         const v3 prev = p;
         bool done = false;
 #if defined(PMAF_FAST_STATS)
-        unsigned why_bits = 0u;
-        unsigned *why = &why_bits;
+        unsigned why_arr[3] = {0u, 0u, 0u};
+        unsigned &why_bits = why_arr[0];
+        unsigned *why = why_arr;
 #else
         unsigned *why = nullptr;
+#endif
+#if defined(PMAF_FAST_STATS)
+        const long long tq0 = clock64();
+        st_cand += pr.n_cand > 0 ? pr.n_cand : 0;
 #endif
         if constexpr (FAST)
           done = fast_step<!DYNAMIC>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec,
@@ -305,6 +313,10 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
           agent_step<!DYNAMIC, OCC == 1>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row,
                                          goal_vec, pr, p, v, min_obs PMAF_T_PASS);
         }
+#if defined(PMAF_FAST_STATS)
+        if (done) st_fast_cyc += clock64() - tq0; else st_gen_cyc += clock64() - tq0, ++st_gen;
+        st_latch_cyc += why_arr[1], st_latch += why_arr[2];
+#endif
         const v3 seg = sub3(p, prev);
         zseg = dot3(seg, seg), has_seg = true;
         if (fused) ws_cost = add_workspace_cost(ws_cost, p, wsp.ws, wsp.k_workspace);
@@ -348,6 +360,14 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
       P.path_len[a] = path_len;
       P.ws_cost[a] = ws_cost;
       P.n_path[a] = n_path;
+#if defined(PMAF_FAST_STATS)
+      if (a < 64 && P.section_cycles) {
+        P.section_cycles[a * 12 + 0] = st_fast_cyc, P.section_cycles[a * 12 + 1] = st_gen_cyc;
+        P.section_cycles[a * 12 + 2] = st_gen, P.section_cycles[a * 12 + 3] = st_cand;
+        P.section_cycles[a * 12 + 4] = steps_run;
+        P.section_cycles[a * 12 + 5] = st_latch_cyc, P.section_cycles[a * 12 + 6] = st_latch;
+      }
+#endif
 #if defined(PMAF_SECTION_TIMERS) && defined(__CUDA_ARCH__)
       if (a < 64 && P.section_cycles)
         for (int q = 0; q < 12; ++q) P.section_cycles[a * 12 + q] = pmaf_sec_[q];

@@ -29,4 +29,14 @@ if __name__ == "__main__":
           f"last rollout {c['last_rollout_ms']:.3f} ms")
     for k, v in m.fast_stats().items():
         print(f"  {k:28s} {v}")
+    import ctypes as C
+    import numpy as np
+    m.lib.pmaf_get_section_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    out = np.zeros((64, 12), dtype=np.int64)
+    m.lib.pmaf_get_section_cycles(m.h, out.ctypes.data_as(C.POINTER(C.c_longlong)))
+    print("  per agent (first 16 of the last rollout): fast cycles/step, general cycles/step, general steps, candidates/step")
+    for a in range(min(16, sc.num_agents)):
+        f, g_, ng, nc, n, lc, ln = out[a, :7]
+        nf = max(n - ng, 1)
+        print(f"   agent {a:2d}: fast {f / nf:7.0f}  general {g_ / max(ng, 1):7.0f}  general steps {ng:4d} of {n:4d}  candidates/step {nc / max(n, 1):5.1f}  cold latches {ln:3d} x {lc / max(ln, 1):6.0f} cycles")
     m.close()
