@@ -206,9 +206,12 @@ int pmaf_get_costs(pmaf_planner *p, double *costs /* [n_agents] */);
  * every obstacle but the trailing sentinel). Optional outputs per tick: best[ticks], next_pos[ticks][3],
  * next_vel[ticks][3]. *seconds = wall time spent inside the ticks (CLOCK_MONOTONIC around each tick).
  * flags: PMAF_DRY_RUN_WAIT_ROLLOUT waits for each tick's rollout inside its timed region (benchmarks: a
- * tick then costs calls + rollout); PMAF_DRY_RUN_FLUSH_L2 evicts the L2 before each tick, untimed. */
+ * tick then costs calls + rollout); PMAF_DRY_RUN_FLUSH_L2 evicts the L2 before each tick, untimed;
+ * PMAF_DRY_RUN_PROFILE: seconds must hold 7 doubles, seconds[1..6] = wall time summed per call
+ * (stop, evaluate, move_real, get + reset, start, final wait). */
 #define PMAF_DRY_RUN_WAIT_ROLLOUT 1
 #define PMAF_DRY_RUN_FLUSH_L2 2
+#define PMAF_DRY_RUN_PROFILE 4
 int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_pos, const double *obs_vel, const double *obs_rad,
                  int n_feed, double feed_frequency, double delta_t, double k_goal_dist, double k_path_len,
                  double k_safe_dist, double k_workspace, const double ws_limits[6], int flags, double *seconds,

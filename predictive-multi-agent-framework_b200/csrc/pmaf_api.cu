@@ -74,16 +74,6 @@ struct DevBuf {
   }
 };
 
-// Everything a tick reads back lives in ONE device block with the layout of its pinned host mirror, so
-// that each call's results come back in a single small copy (eval + best; real + its path; all three).
-struct HostOut {
-  EvalResult eval;
-  DeviceBest best;
-  RealState real;
-  double real_path[256 * 3];
-  unsigned long long steps[16];
-};
-
 struct pmaf_planner {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -143,7 +133,9 @@ struct pmaf_planner {
   // pinned staging
   double *h_stage = nullptr;
   size_t h_stage_doubles = 0;
-  HostOut *h_out = nullptr;
+  HostOut *h_out = nullptr;      // pinned + mapped
+  HostOut *h_out_dev = nullptr;  // the same block as the device sees it
+  unsigned long long ticket = 0;
   bool stage_busy = false;
   // rng for RandomCfAgent vectors
   bool seeded = false;
@@ -277,6 +269,21 @@ static int finish_rollout(pmaf_planner *p) {
   return harvest_timing(p, p->roll_slot, true);
 }
 
+// wait for the ticket a small kernel publishes in the mapped host block after storing its results there
+static int wait_ticket(pmaf_planner *p, int which, unsigned long long ticket) {
+  volatile unsigned long long *flag = &p->h_out->seq[which];
+  for (unsigned spins = 1; *flag != ticket; ++spins) {
+    if ((spins & 0xfffu) == 0u) {  // a failed launch or a trapped kernel never publishes: ask the stream now and then
+      const cudaError_t e = cudaStreamQuery(p->stream);
+      if (e == cudaErrorNotReady) continue;
+      if (e != cudaSuccess) return fail(PMAF_ERR_CUDA, "stream failed while waiting for a result: %s", cudaGetErrorString(e));
+      if (*flag != ticket) return fail(PMAF_ERR_CUDA, "a result ticket never arrived although the stream is idle");
+    }
+  }
+  __sync_synchronize();
+  return 0;
+}
+
 // ---- NCCL (dlopen) ----------------------------------------------------------------------------------------------
 struct NcclApi {
   void *handle = nullptr;
@@ -365,8 +372,9 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(cudaEventCreateWithFlags(&p->ev_stage, cudaEventDisableTiming));
   CU(cudaEventCreate(&p->ev_t0));
   CU(cudaEventCreate(&p->ev_t1));
-  CU(cudaMallocHost(&p->h_out, sizeof(HostOut)));
+  CU(cudaHostAlloc(&p->h_out, sizeof(HostOut), cudaHostAllocMapped));
   memset(p->h_out, 0, sizeof(HostOut));
+  CU(cudaHostGetDevicePointer(&p->h_out_dev, p->h_out, 0));
   CU(p->d_out.resize(1));
   p->eval.alias(&p->d_out.p->eval, 1), p->best.alias(&p->d_out.p->best, 1), p->real.alias(&p->d_out.p->real, 1);
   p->real_path_out.alias(p->d_out.p->real_path, 256 * 3), p->step_counter.alias(p->d_out.p->steps, 16);
@@ -785,12 +793,15 @@ static int launch_evaluate(pmaf_planner *p, const CostParams &C) {
   p->last_cost = C, p->have_cost = true;
   const int threads = p->A >= 1024 ? 1024 : std::max(32, ((p->A + 31) / 32) * 32);
   ArgminRecord *rec = reinterpret_cast<ArgminRecord *>(p->rec.p);
-  if (p->world == 1)
-    return launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec, p->eval.p, 1);
+  if (p->world == 1) {
+    p->ctr.d2h_bytes += sizeof(EvalResult) + sizeof(DeviceBest);  // stored by the kernel into the mapped host block
+    return launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec, p->eval.p, 1,
+                  p->h_out_dev, ++p->ticket);
+  }
   // sharded: local scan -> ONE all-gather of (record + candidate random vectors) -> replicated selection
   REQUIRE(p->nccl != nullptr, PMAF_ERR_STATE, "sharded planner without an NCCL communicator (pmaf_nccl_init)");
   if (int rc = launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec,
-                      p->eval.p, 0))
+                      p->eval.p, 0, (HostOut *)nullptr, 0ull))
     return rc;
   const size_t bytes = argmin_record_bytes(p->O);
   NC(g_nccl.AllGather(p->rec.p, p->rec_all.p, bytes, ncclChar, (ncclComm_t)p->nccl, p->stream));
@@ -821,8 +832,12 @@ extern "C" int pmaf_evaluate_agents(pmaf_planner *p, int n_obs, const double *ob
   static_assert(offsetof(HostOut, best) == sizeof(EvalResult) && offsetof(HostOut, real) == sizeof(EvalResult) + sizeof(DeviceBest) &&
                     offsetof(HostOut, real_path) == offsetof(HostOut, real) + sizeof(RealState),
                 "HostOut members must be contiguous");
-  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
-  CU(cudaStreamSynchronize(p->stream));
+  if (p->world == 1) {
+    if (int rc = wait_ticket(p, 0, p->ticket)) return rc;
+  } else {
+    if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+  }
   p->h_eval = p->h_out->eval, p->h_best = p->h_out->best;
   *best_index = p->h_eval.best_index;
   return 0;
@@ -862,6 +877,8 @@ static int launch_real(pmaf_planner *p, int n_obs, double delta_t, int steps, in
   r.delta_t = delta_t, r.steps = steps, r.agent_id = agent_id_global, r.eval = p->eval.p;
   r.path_out = p->real_path_out.p;
   for (int i = 0; i < 3; ++i) r.goal[i] = p->goal[i];
+  r.host = p->h_out_dev, r.ticket = ++p->ticket;
+  p->ctr.d2h_bytes += sizeof(RealState) + (size_t)steps * 3 * sizeof(double);  // stored by the kernel into the host block
   return launch(p, real_agent_kernel, dim3(1), dim3(32), 0, d, r);
 }
 
@@ -881,8 +898,7 @@ extern "C" int pmaf_move_real_agent(pmaf_planner *p, int n_obs, const double *ob
   for (int done = 0; done < steps;) {
     const int chunk = std::min(steps - done, 256);
     if (int rc = launch_real(p, n_obs, delta_t, chunk, agent_id)) return rc;
-    if (int rc = d2h(p, &p->h_out->real, p->real.p, sizeof(RealState) + (size_t)chunk * 3 * sizeof(double))) return rc;
-    CU(cudaStreamSynchronize(p->stream));
+    if (int rc = wait_ticket(p, 1, p->ticket)) return rc;
     p->h_real = p->h_out->real;
     p->real_path.insert(p->real_path.end(), p->h_out->real_path, p->h_out->real_path + (size_t)chunk * 3);
     done += chunk;
@@ -950,11 +966,15 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, p->h_real.pos)) return rc;
   p->fused_valid = true;
   if (int rc = launch_reset(p, true, true, nullptr, n_obs, p->live_pos.p, p->live_vel.p, true, true)) return rc;
-  if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest) + sizeof(RealState))) return rc;
-  CU(cudaEventRecord(p->ev_d2h, p->stream));
+  const unsigned long long real_ticket = p->ticket;  // launch_real published last
+  if (p->world > 1) {  // the sharded selection kernel does not write the host block
+    if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
+    CU(cudaEventRecord(p->ev_d2h, p->stream));
+  }
   p->obstacles_advanced = false;
   if (int rc = launch_rollout(p)) return rc;
-  CU(cudaEventSynchronize(p->ev_d2h));
+  if (p->world > 1) CU(cudaEventSynchronize(p->ev_d2h));
+  if (int rc = wait_ticket(p, 1, real_ticket)) return rc;
   p->h_eval = p->h_out->eval, p->h_best = p->h_out->best, p->h_real = p->h_out->real;
   p->real_path.insert(p->real_path.end(), p->h_real.pos, p->h_real.pos + 3);
   if (best_index) *best_index = p->h_eval.best_index;
@@ -978,29 +998,47 @@ extern "C" int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_p
   REQUIRE(ticks >= 0 && obs_pos && obs_vel && obs_rad && ws_limits && n_feed >= 0 && n_feed <= n_obs, PMAF_ERR_ARG,
           "pmaf_dry_run: bad argument");
   double total = 0.0;
+  REQUIRE(!(flags & PMAF_DRY_RUN_PROFILE) || seconds, PMAF_ERR_ARG, "pmaf_dry_run: PMAF_DRY_RUN_PROFILE needs seconds[7]");
+  if (flags & PMAF_DRY_RUN_PROFILE)
+    for (int k = 1; k < 7; ++k) seconds[k] = 0.0;
   for (int t = 0; t < ticks; ++t) {
     if (flags & PMAF_DRY_RUN_FLUSH_L2) {
       if (int rc = pmaf_flush_l2(p)) return rc;
     }
     if (flags & (PMAF_DRY_RUN_FLUSH_L2 | PMAF_DRY_RUN_WAIT_ROLLOUT)) {  // drain before the clock starts
       if (int rc = pmaf_stop_prediction(p)) return rc;
+      CU(cudaStreamSynchronize(p->stream));  // the flush, too
     }
     timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
+    timespec tc = t0;
+    auto lap = [&](int k) {  // PMAF_DRY_RUN_PROFILE: seconds[1 + k] accumulates the wall time of call k
+      if (!(flags & PMAF_DRY_RUN_PROFILE)) return;
+      timespec tn;
+      clock_gettime(CLOCK_MONOTONIC, &tn);
+      seconds[1 + k] += (double)(tn.tv_sec - tc.tv_sec) + 1e-9 * (double)(tn.tv_nsec - tc.tv_nsec);
+      tc = tn;
+    };
     int b = 0;
     double pos[3], vel[3];
     if (int rc = pmaf_stop_prediction(p)) return rc;
+    lap(0);
     if (int rc = pmaf_evaluate_agents(p, n_obs, obs_pos, obs_vel, obs_rad, k_goal_dist, k_path_len, k_safe_dist, k_workspace,
                                       ws_limits, &b))
       return rc;
+    lap(1);
     if (int rc = pmaf_move_real_agent(p, n_obs, obs_pos, obs_vel, obs_rad, delta_t, 1, b)) return rc;
+    lap(2);
     if (int rc = pmaf_get_next_position(p, pos)) return rc;
     if (int rc = pmaf_get_next_velocity(p, vel)) return rc;
     if (int rc = pmaf_reset_agents(p, pos, vel, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+    lap(3);
     if (int rc = pmaf_start_prediction(p)) return rc;
+    lap(4);
     if (flags & PMAF_DRY_RUN_WAIT_ROLLOUT) {
       if (int rc = pmaf_stop_prediction(p)) return rc;
     }
+    lap(5);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     total += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     if (best) best[t] = b;

@@ -97,6 +97,20 @@ struct EvalResult {
   double best_cost, argmin_cost;
 };
 
+// Everything a tick reads back lives in ONE device block with the layout of its pinned host mirror, so
+// that each call's results come back in a single small copy (eval + best; real + its path; all three).
+struct HostOut {
+  EvalResult eval;
+  DeviceBest best;
+  RealState real;
+  double real_path[256 * 3];
+  unsigned long long steps[16];
+  // Host mirror only (pinned, mapped): the small kernels of a tick store their results straight into it and
+  // then publish a ticket; the host polls the ticket instead of enqueueing a copy and synchronising the
+  // stream (a launch + copy + sync round trip costs 30-50 us, two of them per call-by-call tick).
+  volatile unsigned long long seq[2];  // [0] evaluate, [1] real agent
+};
+
 struct PlannerDev {  // kernel argument, passed by value
   int n_agents;      // local agents
   int first_agent;   // global index of local agent 0

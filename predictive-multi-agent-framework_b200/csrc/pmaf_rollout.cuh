@@ -503,7 +503,7 @@ __host__ __device__ inline size_t argmin_record_bytes(int n_obs) {
 // hysteresis and incumbent update.
 __global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, const CostParams C, DeviceBest *best,
                                                         double *best_random, ArgminRecord *rec, EvalResult *out,
-                                                        int finalize) {
+                                                        int finalize, HostOut *host, unsigned long long ticket) {
   __shared__ double s_cost[32];
   __shared__ int s_idx[32];
   const v3 goal = ld3(P.goal);
@@ -578,6 +578,13 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, cons
       best->id = min_idx + 1;
       best->type = agent_type_of_index(min_idx);
     }
+    if (host) {  // zero-copy result + ticket (see HostOut)
+      host->eval.best_index = result, host->eval.argmin_index = min_idx, host->eval.incumbent_changed = take;
+      host->eval.pad = 0, host->eval.best_cost = out->best_cost, host->eval.argmin_cost = min_cost;
+      host->best.present = best->present, host->best.id = best->id, host->best.type = best->type, host->best.pad = 0;
+      __threadfence_system();
+      host->seq[0] = ticket;
+    }
   }
 }
 
@@ -633,6 +640,8 @@ struct RealArgs {
   const EvalResult *eval;
   double *path_out;       // [steps][3] position after every step (RealCfAgent::setPosition appends)
   double goal[3];
+  HostOut *host;          // zero-copy result + ticket (see HostOut), or null
+  unsigned long long ticket;
 };
 
 // one warp
@@ -671,10 +680,18 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
       g.sync();
     }
     finish_step(em, force, k_goal_scale, sn, obs.pos(R.n_obs - 1), R.delta_t, k, p, v);
-    if (g.gl == 0) st3(R.path_out + 3 * s, p);
+    if (g.gl == 0) {
+      st3(R.path_out + 3 * s, p);
+      if (R.host) st3(R.host->real_path + 3 * s, p);
+    }
   }
   if (g.gl == 0 && R.steps > 0) {
     st3(R.real->pos, p), st3(R.real->vel, v), st3(R.real->force, force);
+    if (R.host) {
+      st3(R.host->real.pos, p), st3(R.host->real.vel, v), st3(R.host->real.force, force), st3(R.host->real.init_pos, init_pos);
+      __threadfence_system();
+      R.host->seq[1] = R.ticket;
+    }
   }
 }
 

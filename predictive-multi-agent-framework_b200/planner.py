@@ -255,20 +255,22 @@ class CfManager:
         return best.value, p, v
 
     def dry_run(self, ticks, obs_pos, obs_vel, obs_rad, n_feed, delta_t, k_goal_dist, k_path_len, k_safe_dist,
-                k_workspace, ws_limits, feed_frequency=100.0, wait_rollout=False, flush_l2=False):
+                k_workspace, ws_limits, feed_frequency=100.0, wait_rollout=False, flush_l2=False, profile=None):
         """`ticks` planCallbacks in the library's C++ host loop (pmaf_dry_run) on HOST obstacle arrays; obs_pos is
         advanced in place by the obstacle feed. Returns (seconds inside the ticks, best[ticks], next_pos, next_vel)."""
         assert obs_pos.dtype == np.float64 and obs_pos.flags["C_CONTIGUOUS"]
         ov, orad = _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
         best = np.zeros(max(ticks, 1), dtype=np.int32)
         npos, nvel = np.zeros((max(ticks, 1), 3)), np.zeros((max(ticks, 1), 3))
-        sec = C.c_double()
-        flags = (1 if wait_rollout else 0) | (2 if flush_l2 else 0)
+        sec = (C.c_double * 7)()
+        flags = (1 if wait_rollout else 0) | (2 if flush_l2 else 0) | (4 if profile is not None else 0)
         self._check(self.lib.pmaf_dry_run(self.h, int(ticks), len(orad), _d(obs_pos), _d(ov), _d(orad), int(n_feed),
                                           float(feed_frequency), float(delta_t), float(k_goal_dist), float(k_path_len),
                                           float(k_safe_dist), float(k_workspace), _d(_f64(ws_limits, (6,))), flags,
-                                          C.byref(sec), _i(best), _d(npos), _d(nvel)))
-        return sec.value, best[:ticks], npos[:ticks], nvel[:ticks]
+                                          sec, _i(best), _d(npos), _d(nvel)))
+        if profile is not None:  # per-call wall time: stop, evaluate, move_real, get + reset, start, final wait
+            profile[:] = [sec[k] for k in range(1, 7)]
+        return sec[0], best[:ticks], npos[:ticks], nvel[:ticks]
 
     # ---- getters ----------------------------------------------------------------------------------
     def _vec3(self, fn):
