@@ -94,11 +94,13 @@ def measured_peaks():
 
 
 def measured_traffic(workload):
-    """dram__bytes_read + dram__bytes_write of the rollout kernel, per launch, from the committed
-    `ncu --set full` summary of the same workload (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", f"r01_ncu_rollout_{workload}_summary.json")
+    """dram__bytes_read + dram__bytes_write of the rollout kernel, per launch, from the newest committed
+    `ncu --set full` summary of the same workload (profiles/r*_ncu_rollout_<workload>_summary.json), or None."""
+    import glob
+
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_rollout_{workload}_summary.json")))
     try:
-        return json.load(open(path)).get("dram_bytes_per_launch")
+        return json.load(open(paths[-1])).get("dram_bytes_per_launch") if paths else None
     except (OSError, ValueError):
         return None
 
