@@ -71,6 +71,21 @@ __device__ __forceinline__ double exp_main(FastMath &m, double x) {
   return fma(scale, tmp, scale);
 }
 
+// path point store by lane 0 as predicated instructions (the compiler makes `if (lane == 0 && pending)` a
+// branch, which would end the basic block the store shares with the next step's prologue)
+__device__ __forceinline__ void st3_if(double *ptr, v3 a, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %4, 0;\n"
+      "@q st.global.f64 [%0], %1;\n"
+      "@q st.global.f64 [%0+8], %2;\n"
+      "@q st.global.f64 [%0+16], %3;\n"
+      "}\n" ::"l"(ptr),
+      "d"(a.x), "d"(a.y), "d"(a.z), "r"((unsigned)pred)
+      : "memory");
+}
+
 // One step of one agent by one full warp. Returns true when the step was taken (p, v, min_obs updated);
 // false: nothing changed, run the general step. pr = this step's prologue (norms, unit vectors, broad phase).
 template <bool STATIC_VEL>
@@ -78,7 +93,7 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
                                           const uint16_t *cand, double *fbuf, const KnownBits &known, int type,
                                           const AgentConsts &c, const FastConsts &fc, v3 init_pos,
                                           double *rot_row, const double *random_row, v3 goal_vec, const Prologue &pr,
-                                          v3 &p, v3 &v, double &min_obs, unsigned *why = nullptr) {
+                                          v3 &p, v3 &v, double &min_obs, unsigned *why = nullptr, bool step_on = true) {
   // why (developer statistics, PMAF_FAST_STATS builds): bit mask of the reasons a step was not taken
 #define PMAF_RARE(bit, cond)                   \
   do {                                         \
@@ -97,7 +112,7 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
   const bool gate_open = !(sn.dist_goal < c.approach_dist) & !((sn.vn < c.half_vmax) & near_start);
   // ONE branch decides between this path and the general step: a closed gate (no field pass: the general
   // step is as short), no or too many candidates, an unusable configuration
-  if (!(fc.usable & (n_cand > 0) & (n_cand <= 32) & gate_open & !start_ambiguous)) {
+  if (!(step_on & fc.usable & (n_cand > 0) & (n_cand <= 32) & gate_open & !start_ambiguous)) {
     if (why) *why |= 1u;
     return false;
   }

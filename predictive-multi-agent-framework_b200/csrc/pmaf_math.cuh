@@ -575,6 +575,24 @@ PMAF_HD double add_workspace_cost(double cost, v3 q, const double *ws, double k_
   return cost;
 }
 
+// The same term without a branch (selects; adding +0.0 for an axis inside its limits is exact because the
+// running cost is a sum of squares starting at +0.0 and can never be -0.0): it can share a basic block
+// with other work. NaN coordinates add nothing, as in the reference (both comparisons false).
+PMAF_HD double add_workspace_cost_bf(double cost, v3 q, const double *ws, double k_workspace) {
+  const double qs[3] = {q.x, q.y, q.z};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 3; ++a) {
+    const bool hi = qs[a] > ws[2 * a], lo = qs[a] < ws[2 * a + 1];
+    const double lim = hi ? ws[2 * a] : ws[2 * a + 1];
+    double t = fabs(qs[a] - lim) * k_workspace;
+    t = (hi | lo) ? t : 0.0;
+    cost += t * t;
+  }
+  return cost;
+}
+
 // remaining terms of the per-agent cost, cf_manager.cpp:324-333
 PMAF_HD double finish_cost(double ws_cost, double goal_dist, double approach_dist, double k_goal_dist,
                            double path_len, double k_path_len, double k_safe_dist, double min_obs_dist) {

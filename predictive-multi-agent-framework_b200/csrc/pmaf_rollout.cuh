@@ -273,6 +273,57 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
 #if defined(PMAF_FAST_STATS)
   long long st_fast_cyc = 0, st_gen_cyc = 0, st_gen = 0, st_cand = 0, st_latch_cyc = 0, st_latch = 0;
 #endif
+  if constexpr (FAST && !DYNAMIC) {
+    // Latency build, static scene: the loop is rotated — the commit of the previous step (path point,
+    // workspace cost, counters) shares ONE basic block with this step's prologue, and one branch decides
+    // between the straight-line step and everything else (termination, closed gate, rare events).
+    if (alive) {
+      v3 prev = p;
+      bool pending = false;  // a step was taken whose commit is outstanding
+      for (;;) {
+        const v3 seg = sub3(p, prev);
+        const double zs = dot3(seg, seg);
+        const v3 goal_vec = sub3(goal, p);
+        const Prologue pr = step_prologue<true, true>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k);
+        const StepNorms &sn = pr.sn;
+        path_len += sn.seg_len;  // getPathLength term (:29), in path order; 0 while nothing is pending
+        if (fused) {
+          const double w = add_workspace_cost_bf(ws_cost, p, wsp.ws, wsp.k_workspace);
+          ws_cost = pending ? w : ws_cost;
+        }
+        st3_if(path_row + (size_t)n_path * 3, p, pending & (g.gl == 0));
+        n_path += pending ? 1 : 0, steps_run += pending ? 1 : 0;
+        const bool step_on = sn.dist_goal > 0.1 && n_path < max_steps;  // :310-311
+        prev = p;
+#if defined(PMAF_FAST_STATS)
+        unsigned why_arr[3] = {0u, 0u, 0u};
+        unsigned *why = why_arr;
+        const long long tq0 = clock64();
+        st_cand += pr.n_cand > 0 ? pr.n_cand : 0;
+#else
+        unsigned *why = nullptr;
+#endif
+        const bool done = fast_step<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
+                                          goal_vec, pr, p, v, min_obs, why, step_on);
+        if (!done) {
+          if (!step_on) break;
+          ++general_steps;
+#if defined(PMAF_FAST_STATS)
+          if (g.gl == 0)
+            for (int b = 0; b < 12; ++b)
+              if (why_arr[0] >> b & 1u) atomicAdd(P.step_counter + 4 + b, 1ull);
+#endif
+          agent_step<true, true>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, pr,
+                                 p, v, min_obs PMAF_T_PASS);
+        }
+#if defined(PMAF_FAST_STATS)
+        if (done) st_fast_cyc += clock64() - tq0; else st_gen_cyc += clock64() - tq0, ++st_gen;
+        st_latch_cyc += why_arr[1], st_latch += why_arr[2];
+#endif
+        pending = true;
+      }
+    }
+  } else
   if (DYNAMIC || alive)  // static scenes: an agent's warp leaves the loop directly when its rollout ends
   for (;;) {
     if (!DYNAMIC || alive) {
