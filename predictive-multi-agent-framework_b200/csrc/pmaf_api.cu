@@ -195,8 +195,16 @@ static ObstacleImage layout_image(int n_obs, bool dynamic) {
     im.off_dz = off, off += col;
   }
   im.off_bp = off, off += (uint32_t)((size_t)n_obs * sizeof(float4));
+  im.off_nn = off, off += (uint32_t)(((size_t)n_obs * sizeof(uint16_t) + 15) & ~(size_t)15);
+  im.nn_valid = 0;
   im.bytes = (off + 15u) & ~15u;
   return im;
+}
+
+// The OBSTACLE / GOAL_OBSTACLE agents (global indices 2 and 3) look up the nearest other obstacle of every
+// obstacle they detect; in a static scene that is a per-tick table, built by spare blocks of reset_kernel.
+static int wants_nn_table(const pmaf_planner *p, const ObstacleImage &im) {
+  return (!im.dynamic && p->O >= 3 && p->first_agent <= 3 && p->first_agent + p->A > 2) ? 1 : 0;
 }
 
 static bool any_nonzero(const std::vector<double> &v) {
@@ -472,8 +480,10 @@ static int launch_reset(pmaf_planner *p, bool do_agents, bool from_real, const d
   r.set_known = set_known ? 1 : 0, r.reset_velocity = reset_velocity ? 1 : 0;
   r.do_agents = do_agents ? 1 : 0;
   const int block = 128;
-  const int grid = do_agents ? (p->A + block - 1) / block : 1;
-  return launch(p, reset_kernel, dim3(grid), dim3(block), 0, d, r);
+  r.agent_blocks = do_agents ? (p->A + block - 1) / block : 1;
+  // nearest-neighbour table: one warp per obstacle row, spread over extra blocks (they overlap block 0)
+  const int nn_blocks = p->img.nn_valid ? std::min(64, (p->O - 1 + 3) / 4) : 0;
+  return launch(p, reset_kernel, dim3(r.agent_blocks + nn_blocks), dim3(block), 0, d, r);
 }
 
 extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, int n_obs, const double *obs_pos,
@@ -624,6 +634,7 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
   p->obstacles_advanced = false;
   p->agents_touched = true;
   p->img = layout_image((int)O, any_nonzero(p->h_obs_vel));
+  p->img.nn_valid = wants_nn_table(p, p->img);
   CU(p->image.resize(p->img.bytes));
   p->margin = broad_phase_margin(p, p->mgr_init_pos);
 
@@ -910,7 +921,8 @@ static int refresh_obstacle_copy(pmaf_planner *p, int n_obs, const double *obs_p
                                  const double *pos) {
   memcpy(p->h_obs_pos.data(), obs_pos, (size_t)n_obs * 3 * sizeof(double));
   memcpy(p->h_obs_vel.data(), obs_vel, (size_t)n_obs * 3 * sizeof(double));
-  const ObstacleImage im = layout_image(p->O, any_nonzero(p->h_obs_vel));
+  ObstacleImage im = layout_image(p->O, any_nonzero(p->h_obs_vel));
+  im.nn_valid = wants_nn_table(p, im);
   if (im.bytes != p->img.bytes) CU(p->image.resize(im.bytes));
   p->img = im;
   p->margin = broad_phase_margin(p, pos);

@@ -93,7 +93,8 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
                                           const uint16_t *cand, double *fbuf, const KnownBits &known, int type,
                                           const AgentConsts &c, const FastConsts &fc, v3 init_pos,
                                           double *rot_row, const double *random_row, v3 goal_vec, const Prologue &pr,
-                                          v3 &p, v3 &v, double &min_obs, unsigned *why = nullptr, bool step_on = true) {
+                                          v3 &p, v3 &v, double &min_obs, unsigned *why = nullptr, bool step_on = true,
+                                          const uint16_t *nn_table = nullptr) {
   // why (developer statistics, PMAF_FAST_STATS builds): bit mask of the reasons a step was not taken
 #define PMAF_RARE(bit, cond)                   \
   do {                                         \
@@ -168,7 +169,9 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
         // out-of-line call here costs more in register saves than the work itself
         FastMath fscan, frot;
         int nn = 0;
-        if (fc.tbits & kTNeedsNN) {  // nearest other field obstacle, serial-scan semantics (:434-446)
+        if ((fc.tbits & kTNeedsNN) && nn_table) {  // static scene: per-tick table built by reset_kernel
+          nn = nn_table[i];
+        } else if (fc.tbits & kTNeedsNN) {  // nearest other field obstacle, serial-scan semantics (:434-446)
           const int n_field = P.n_obs - 1;
           while (todo) {
             const int src = __ffs(todo) - 1;

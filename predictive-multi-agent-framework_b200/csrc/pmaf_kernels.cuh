@@ -75,6 +75,9 @@ struct ObstacleImage {
   uint32_t off_vx, off_vy, off_vz;  // double[O]  velocities           (dynamic only)
   uint32_t off_dx, off_dy, off_dz;  // double[O]  velocity * dt        (dynamic only, :273)
   uint32_t off_bp;                  // float4[O]  broad phase: x, y, z, (shell + rs + margin)^2
+  uint32_t off_nn;                  // uint16[O]  nearest other field obstacle of each obstacle (:434-446), static
+                                    //            scenes with OBSTACLE / GOAL_OBSTACLE agents only (nn_valid)
+  int nn_valid;
   uint32_t bytes;                   // image size (multiple of 16)
 };
 

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
 #if defined(PMAF_FAST_STATS)
   long long st_fast_cyc = 0, st_gen_cyc = 0, st_gen = 0, st_cand = 0, st_latch_cyc = 0, st_latch = 0;
 #endif
+  const uint16_t *nn_table = P.img.nn_valid ? reinterpret_cast<const uint16_t *>(img + P.img.off_nn) : nullptr;
   if constexpr (FAST && !DYNAMIC) {
     // Latency build, static scene: the loop is rotated — the commit of the previous step (path point,
     // workspace cost, counters) shares ONE basic block with this step's prologue, and one branch decides
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         unsigned *why = nullptr;
 #endif
         const bool done = fast_step<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
-                                          goal_vec, pr, p, v, min_obs, why, step_on);
+                                          goal_vec, pr, p, v, min_obs, why, step_on, nn_table);
         if (!done) {
           if (!step_on) break;
           ++general_steps;
@@ -457,11 +458,32 @@ struct ResetArgs {
   int do_agents;              // 0: only rebuild the staging image
   int set_known;              // 1: known := real agent's flags for the passed obstacles
   int reset_velocity;         // 1: vel := clamp(v); min_obs_dist := shell
+  int agent_blocks;           // blocks [0, agent_blocks) do the work above; further blocks build the nn table
+};
+
+// the obstacle positions a rollout will start from, as block 0 of reset_kernel is about to write them
+struct ResetObstacles {
+  const double *new_pos, *old_pos;
+  int n_update;
+  PMAF_HDT v3 pos(int i) const { return i < n_update ? ld3(new_pos + 3 * i) : ld3(old_pos + 3 * i); }
 };
 
 // grid: ceil(A / blockDim) blocks (1 block when !do_agents); block 0 also rebuilds the staging image.
 __global__ void __launch_bounds__(128) reset_kernel(const PlannerDev P, const ResetArgs R) {
   __shared__ uint32_t s_bits[kMaxObstacles / 32], s_keep[kMaxObstacles / 32];
+  if ((int)blockIdx.x >= R.agent_blocks) {  // nearest-neighbour table of a static scene (ObstacleImage::off_nn)
+    const Group<32> g;
+    ResetObstacles obs;
+    obs.new_pos = R.new_pos, obs.old_pos = R.obs_pos, obs.n_update = R.n_obs_update;
+    uint16_t *nn = reinterpret_cast<uint16_t *>(R.image + P.img.off_nn);
+    const int n_field = P.n_obs - 1;
+    const int warps = (gridDim.x - R.agent_blocks) * (blockDim.x / 32);
+    for (int row = (blockIdx.x - R.agent_blocks) * (blockDim.x / 32) + threadIdx.x / 32; row < n_field; row += warps) {
+      const int found = nearest_other_obstacle(g, obs, n_field, row);
+      if (g.gl == 0) nn[row] = (uint16_t)found;
+    }
+    return;
+  }
   if (blockIdx.x == 0) {
     double *px = reinterpret_cast<double *>(R.image + P.img.off_px);
     double *py = reinterpret_cast<double *>(R.image + P.img.off_py);
