@@ -115,6 +115,29 @@ PMAF_HDT Prologue step_prologue(const G &g, const float4 *bp, int n_field, uint1
   return pr;
 }
 
+// The same without the in-place fallback (rotated loop of the latency build): an operand outside FastMath's
+// range only raises `bad`; the caller re-evaluates with redo_prologue_exact on its slow path, so the hot
+// block carries no reconvergence region.
+template <bool STATIC_VEL, class G>
+PMAF_HDT Prologue step_prologue_nofallback(const G &g, const float4 *bp, int n_field, uint16_t *cand, v3 goal_vec, v3 p,
+                                           v3 v, double zseg, bool has_seg, const AgentConsts &c, bool &bad) {
+  Prologue pr;
+  FastMath fm;
+  pr.sn = step_norms(fm, goal_vec, v, zseg, has_seg, c);
+  step_units<STATIC_VEL>(fm, goal_vec, v, pr.sn, pr.ghat, pr.nv_static);
+  const bool small = n_field <= kBroadUnrolledRounds * G::kLanes;
+  pr.n_cand = broad_phase_unrolled<kBroadUnrolledRounds>(g, bp, small ? n_field : 0, p, cand);
+  if (!small) pr.n_cand = -1;
+  bad = fm.bad();
+  return pr;
+}
+template <bool STATIC_VEL>
+PMAF_HDT void redo_prologue_exact(Prologue &pr, v3 goal_vec, v3 v, double zseg, bool has_seg, const AgentConsts &c) {
+  ExactMath em;
+  pr.sn = step_norms(em, goal_vec, v, zseg, has_seg, c);
+  step_units<STATIC_VEL>(em, goal_vec, v, pr.sn, pr.ghat, pr.nv_static);
+}
+
 }  // namespace pmaf
 #include "pmaf_fast.cuh"
 namespace pmaf {
@@ -260,6 +283,10 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace, rz);
   // latency build, one warp per agent: common steps take the straight-line path (pmaf_fast.cuh)
   constexpr bool FAST = OCC == 1 && LPA == 32;
+  if (FAST && have_agent) {  // the agent's rotation-vector row into L1 now: its first uses sit on the critical path
+    const char *row = reinterpret_cast<const char *>(rot_row);
+    for (int off = g.gl * 128; off < P.n_obs * 24; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + off));
+  }
   FastConsts fc;
   if (FAST) fc = make_fast_consts(k, type, rz);
   const unsigned long long t0 = global_timer_ns();
@@ -285,8 +312,10 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         const v3 seg = sub3(p, prev);
         const double zs = dot3(seg, seg);
         const v3 goal_vec = sub3(goal, p);
-        const Prologue pr = step_prologue<true, true>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k);
+        bool pr_bad;
+        Prologue pr = step_prologue_nofallback<true>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k, pr_bad);
         const StepNorms &sn = pr.sn;
+        const double path_len_before = path_len;
         path_len += sn.seg_len;  // getPathLength term (:29), in path order; 0 while nothing is pending
         if (fused) {
           const double w = add_workspace_cost_bf(ws_cost, p, wsp.ws, wsp.k_workspace);
@@ -294,7 +323,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         }
         st3_if(path_row + (size_t)n_path * 3, p, pending & (g.gl == 0));
         n_path += pending ? 1 : 0, steps_run += pending ? 1 : 0;
-        const bool step_on = sn.dist_goal > 0.1 && n_path < max_steps;  // :310-311
+        bool step_on = (sn.dist_goal > 0.1) & (n_path < max_steps) & !pr_bad;  // :310-311
         prev = p;
 #if defined(PMAF_FAST_STATS)
         unsigned why_arr[3] = {0u, 0u, 0u};
@@ -307,6 +336,11 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         const bool done = fast_step<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
                                           goal_vec, pr, p, v, min_obs, why, step_on, nn_table);
         if (!done) {
+          if (pr_bad) {  // an operand outside FastMath's range: the prologue again with the IEEE built-ins
+            redo_prologue_exact<true>(pr, goal_vec, v, zs, pending, k);
+            path_len = path_len_before + sn.seg_len;
+            step_on = sn.dist_goal > 0.1 && n_path < max_steps;
+          }
           if (!step_on) break;
           ++general_steps;
 #if defined(PMAF_FAST_STATS)
