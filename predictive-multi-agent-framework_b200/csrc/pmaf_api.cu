@@ -280,13 +280,24 @@ static int finish_rollout(pmaf_planner *p) {
 // wait for the ticket a small kernel publishes in the mapped host block after storing its results there
 static int wait_ticket(pmaf_planner *p, int which, unsigned long long ticket) {
   volatile unsigned long long *flag = &p->h_out->seq[which];
+  timespec t0{};
+  bool timed = false;
+  long next_check_us = 2000;  // a failed launch or a trapped kernel never publishes: ask the stream, but rarely
   for (unsigned spins = 1; *flag != ticket; ++spins) {
-    if ((spins & 0xfffu) == 0u) {  // a failed launch or a trapped kernel never publishes: ask the stream now and then
-      const cudaError_t e = cudaStreamQuery(p->stream);
-      if (e == cudaErrorNotReady) continue;
-      if (e != cudaSuccess) return fail(PMAF_ERR_CUDA, "stream failed while waiting for a result: %s", cudaGetErrorString(e));
-      if (*flag != ticket) return fail(PMAF_ERR_CUDA, "a result ticket never arrived although the stream is idle");
+    if ((spins & 0xfffu) != 0u) continue;
+    timespec tn;
+    clock_gettime(CLOCK_MONOTONIC, &tn);
+    if (!timed) {
+      t0 = tn, timed = true;
+      continue;
     }
+    const long us = (long)(tn.tv_sec - t0.tv_sec) * 1000000L + (tn.tv_nsec - t0.tv_nsec) / 1000L;
+    if (us < next_check_us) continue;
+    next_check_us = us + 2000;
+    const cudaError_t e = cudaStreamQuery(p->stream);
+    if (e == cudaErrorNotReady) continue;
+    if (e != cudaSuccess) return fail(PMAF_ERR_CUDA, "stream failed while waiting for a result: %s", cudaGetErrorString(e));
+    if (*flag != ticket) return fail(PMAF_ERR_CUDA, "a result ticket never arrived although the stream is idle");
   }
   __sync_synchronize();
   return 0;
