@@ -252,7 +252,8 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(sc, world, {"lanes_per_agent": c1["lanes_per_agent"],
                                                   "block_threads": c1["block_threads"], "grid": c1["grid_blocks"],
-                                                  "smem_bytes": c1["smem_bytes"], "occupancy_build": c1["occupancy_build"]}),
+                                                  "smem_bytes": c1["smem_bytes"], "occupancy_build": c1["occupancy_build"],
+                                                  "best_agent_exchange": getattr(mgr, "exchange", "none (one GPU)")}),
             "clocks": clocks,
             "e2e": {"value": e2e_steps_all / e2e_s, "unit": "agent-steps/s",
                     "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) / args.steps,

@@ -88,6 +88,14 @@ int pmaf_set_shard(pmaf_planner *p, int n_global, int first_agent, int rank, int
 int pmaf_nccl_unique_id(unsigned char id_out[128]);
 int pmaf_nccl_init(pmaf_planner *p, const unsigned char id[128], int rank, int world);
 int pmaf_set_nccl_comm(pmaf_planner *p, void *nccl_comm);
+/* Best-agent exchange over NVLink peer memory instead of the NCCL all-gather (GPUs of one node, one process
+ * each, at most 16): every rank exports the cudaIpc handle of its exchange block, the host program
+ * distributes the handles (any transport), every rank imports all of them ([world][64], its own entry is
+ * ignored). From then on evaluate_agents / tick run ONE kernel per rank that stores the rank's record
+ * straight into every peer's block, waits for the peers' records and does the replicated selection.
+ * Call both after pmaf_set_shard. If import fails (no peer access), the NCCL path stays in use. */
+int pmaf_p2p_export(pmaf_planner *p, unsigned char handle_out[64]);
+int pmaf_p2p_import(pmaf_planner *p, const unsigned char *handles /* [world][64] */, int rank, int world);
 
 /* CfManager::init (h:93-102, cpp:41-124). n_agents = k_attr.size() (at least one agent — HAD —
  * is always created, cpp:70-72); gains are per agent; the incumbent best agent SURVIVES init

@@ -106,6 +106,11 @@ struct pmaf_planner {
   DevBuf<unsigned char> rec;       // this rank's ArgminRecord + random-vector row
   DevBuf<unsigned char> rec_all;   // all-gathered records [world]
   bool nccl_owned = false;
+  // best-agent exchange over peer memory (pmaf_p2p_export / pmaf_p2p_import); replaces the NCCL all-gather
+  DevBuf<unsigned char> xchg;          // this rank's exchange block
+  unsigned char *peer_xchg[kP2pMaxWorld] = {};
+  bool p2p_ready = false;
+  unsigned long long xseq = 0;
   DevBuf<unsigned long long> step_counter;
   DevBuf<HostOut> d_out;  // eval, best, real, real_path_out, step_counter are views into it
   DevBuf<unsigned char> l2_scratch;
@@ -367,6 +372,56 @@ extern "C" int pmaf_nccl_init(pmaf_planner *p, const unsigned char id_bytes[128]
   return 0;
 }
 
+// ---- best-agent exchange over peer memory (cudaIpc) --------------------------------------------------------------------
+static void p2p_release(pmaf_planner *p) {
+  for (int r = 0; r < kP2pMaxWorld; ++r) {
+    if (p->peer_xchg[r] && p->peer_xchg[r] != p->xchg.p) cudaIpcCloseMemHandle(p->peer_xchg[r]);
+    p->peer_xchg[r] = nullptr;
+  }
+  p->p2p_ready = false;
+}
+
+extern "C" int pmaf_p2p_export(pmaf_planner *p, unsigned char handle_out[64]) {
+  ENTER(p);
+  REQUIRE(handle_out, PMAF_ERR_ARG, "null output");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  p2p_release(p);
+  CU(p->xchg.resize(p2p_block_bytes()));
+  CU(cudaMemsetAsync(p->xchg.p, 0, p2p_block_bytes(), p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, p->xchg.p));
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+
+extern "C" int pmaf_p2p_import(pmaf_planner *p, const unsigned char *handles, int rank, int world) {
+  ENTER(p);
+  REQUIRE(handles && world >= 2 && world <= kP2pMaxWorld && rank >= 0 && rank < world, PMAF_ERR_ARG,
+          "pmaf_p2p_import: bad argument (2 <= world <= %d)", kP2pMaxWorld);
+  REQUIRE(p->xchg.p != nullptr, PMAF_ERR_STATE, "pmaf_p2p_import: call pmaf_p2p_export first");
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      p->peer_xchg[r] = p->xchg.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void *ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      p2p_release(p);
+      (void)cudaGetLastError();
+      return fail(PMAF_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+    p->peer_xchg[r] = static_cast<unsigned char *>(ptr);
+  }
+  p->h_out->p2p_fail = 0;
+  p->xseq = 0;
+  p->p2p_ready = true;
+  return 0;
+}
+
 // ---- lifecycle -------------------------------------------------------------------------------------------------
 extern "C" int pmaf_create(pmaf_planner **out, int device) {
   REQUIRE(out != nullptr, PMAF_ERR_ARG, "pmaf_create: out is null");
@@ -430,6 +485,8 @@ extern "C" int pmaf_destroy(pmaf_planner *p) {
   p->real.release(), p->best.release(), p->eval.release(), p->rec.release(), p->step_counter.release();
   p->rec_all.release();
   p->d_out.release();
+  p2p_release(p);
+  p->xchg.release();
   nccl_release(p);
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -820,11 +877,20 @@ static int launch_evaluate(pmaf_planner *p, const CostParams &C) {
     return launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec, p->eval.p, 1,
                   p->h_out_dev, ++p->ticket);
   }
-  // sharded: local scan -> ONE all-gather of (record + candidate random vectors) -> replicated selection
-  REQUIRE(p->nccl != nullptr, PMAF_ERR_STATE, "sharded planner without an NCCL communicator (pmaf_nccl_init)");
+  // sharded: local scan, then the exchange + replicated selection
   if (int rc = launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, rec,
                       p->eval.p, 0, (HostOut *)nullptr, 0ull))
     return rc;
+  if (p->p2p_ready) {  // ONE kernel: P2P stores into every peer's block over NVLink, wait, select, publish to the host
+    P2pExchange X{};
+    for (int r = 0; r < p->world; ++r) X.peers[r] = p->peer_xchg[r];
+    X.rank = p->rank, X.world = p->world, X.seq = ++p->xseq, X.stride = p2p_slot_stride();
+    p->ctr.collectives++;
+    p->ctr.d2h_bytes += sizeof(EvalResult) + sizeof(DeviceBest);
+    return launch(p, p2p_select_kernel, dim3(1), dim3(256), 0, (const unsigned char *)p->rec.p, X, p->O, p->best.p,
+                  p->best_random.p, p->eval.p, p->h_out_dev, ++p->ticket, (int *)&p->h_out_dev->p2p_fail);
+  }
+  REQUIRE(p->nccl != nullptr, PMAF_ERR_STATE, "sharded planner without an exchange (pmaf_nccl_init or pmaf_p2p_import)");
   const size_t bytes = argmin_record_bytes(p->O);
   NC(g_nccl.AllGather(p->rec.p, p->rec_all.p, bytes, ncclChar, (ncclComm_t)p->nccl, p->stream));
   p->ctr.collectives++;
@@ -854,8 +920,9 @@ extern "C" int pmaf_evaluate_agents(pmaf_planner *p, int n_obs, const double *ob
   static_assert(offsetof(HostOut, best) == sizeof(EvalResult) && offsetof(HostOut, real) == sizeof(EvalResult) + sizeof(DeviceBest) &&
                     offsetof(HostOut, real_path) == offsetof(HostOut, real) + sizeof(RealState),
                 "HostOut members must be contiguous");
-  if (p->world == 1) {
+  if (p->world == 1 || p->p2p_ready) {
     if (int rc = wait_ticket(p, 0, p->ticket)) return rc;
+    REQUIRE(!p->h_out->p2p_fail, PMAF_ERR_NCCL, "best-agent exchange: a peer's record never arrived");
   } else {
     if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
     CU(cudaStreamSynchronize(p->stream));
@@ -990,14 +1057,16 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   p->fused_valid = true;
   if (int rc = launch_reset(p, true, true, nullptr, n_obs, p->live_pos.p, p->live_vel.p, true, true)) return rc;
   const unsigned long long real_ticket = p->ticket;  // launch_real published last
-  if (p->world > 1) {  // the sharded selection kernel does not write the host block
+  const bool copy_eval = p->world > 1 && !p->p2p_ready;
+  if (copy_eval) {  // the NCCL path's selection kernel does not write the host block
     if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
     CU(cudaEventRecord(p->ev_d2h, p->stream));
   }
   p->obstacles_advanced = false;
   if (int rc = launch_rollout(p)) return rc;
-  if (p->world > 1) CU(cudaEventSynchronize(p->ev_d2h));
+  if (copy_eval) CU(cudaEventSynchronize(p->ev_d2h));
   if (int rc = wait_ticket(p, 1, real_ticket)) return rc;
+  REQUIRE(!p->h_out->p2p_fail, PMAF_ERR_NCCL, "best-agent exchange: a peer's record never arrived");
   p->h_eval = p->h_out->eval, p->h_best = p->h_out->best, p->h_real = p->h_out->real;
   p->real_path.insert(p->real_path.end(), p->h_real.pos, p->h_real.pos + 3);
   if (best_index) *best_index = p->h_eval.best_index;

@@ -112,6 +112,7 @@ struct HostOut {
   // then publish a ticket; the host polls the ticket instead of enqueueing a copy and synchronising the
   // stream (a launch + copy + sync round trip costs 30-50 us, two of them per call-by-call tick).
   volatile unsigned long long seq[2];  // [0] evaluate, [1] real agent
+  volatile int p2p_fail;               // set by p2p_select_kernel when a peer's record never arrived
 };
 
 struct PlannerDev {  // kernel argument, passed by value

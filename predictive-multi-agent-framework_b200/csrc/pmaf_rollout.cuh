@@ -387,10 +387,6 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
                                      pr, p, v, min_obs, why);
         if (!done) {
           ++general_steps;
-#if defined(PMAF_EXPERIMENT_NO_GENERAL)
-        }
-        if (false) {
-#endif
 #if defined(PMAF_FAST_STATS)
           if (g.gl == 0)
             for (int b = 0; b < 12; ++b)
@@ -698,19 +694,22 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, cons
 // Sharded planners: after ONE all-gather of the per-rank records every rank repeats the reference's
 // serial scan over the ranks in order (ranks own contiguous ascending agent blocks, so "lowest index
 // wins" is preserved), applies the hysteresis and updates its replica of the incumbent.
-__global__ void __launch_bounds__(256) global_select_kernel(const unsigned char *records, int world, int n_obs,
-                                                            DeviceBest *best, double *best_random,
-                                                            EvalResult *out) {
+// the replicated selection itself: thread 0 scans the per-rank records in rank order, applies the hysteresis
+// and updates this rank's replica of the incumbent; the block then copies the winner's random vectors
+__device__ __forceinline__ void select_over_records(const unsigned char *records, size_t stride, int world, int n_obs,
+                                                    DeviceBest *best, double *best_random, EvalResult *out) {
   __shared__ int s_take, s_min_rank;
-  const size_t stride = argmin_record_bytes(n_obs);
   if (threadIdx.x == 0) {
     double min_cost = 1.7976931348623157e308;
     int min_idx = 0, min_rank = -1;
     double inc_cost = 0.0, cost0 = 0.0;
     bool have_inc = false;
     for (int r = 0; r < world; ++r) {
-      const ArgminRecord *rec = reinterpret_cast<const ArgminRecord *>(records + r * stride);
-      if (rec->min_index != 0x7fffffff && rec->min_cost < min_cost) min_cost = rec->min_cost, min_idx = rec->min_index, min_rank = r;
+      // volatile: the records may have been written by peers over NVLink (p2p_select_kernel); never from L1
+      const volatile ArgminRecord *rec = reinterpret_cast<const volatile ArgminRecord *>(records + r * stride);
+      const double rc = rec->min_cost;
+      const int ri = rec->min_index;
+      if (ri != 0x7fffffff && rc < min_cost) min_cost = rc, min_idx = ri, min_rank = r;
       if (rec->owns_incumbent) inc_cost = rec->incumbent_cost, have_inc = true;
       if (r == 0) cost0 = rec->cost_agent0;
     }
@@ -728,7 +727,89 @@ __global__ void __launch_bounds__(256) global_select_kernel(const unsigned char 
   __syncthreads();
   if (s_take) {
     const double *row = reinterpret_cast<const double *>(records + s_min_rank * stride + sizeof(ArgminRecord));
-    for (int i = threadIdx.x; i < n_obs * 3; i += blockDim.x) best_random[i] = row[i];
+    for (int i = threadIdx.x; i < n_obs * 3; i += blockDim.x) best_random[i] = __ldcg(row + i);
+  }
+}
+
+__global__ void __launch_bounds__(256) global_select_kernel(const unsigned char *records, int world, int n_obs,
+                                                            DeviceBest *best, double *best_random,
+                                                            EvalResult *out) {
+  select_over_records(records, argmin_record_bytes(n_obs), world, n_obs, best, best_random, out);
+}
+
+// ---- best-agent exchange over NVLink peer memory -----------------------------------------------------------------------
+// Instead of an NCCL all-gather between the local scan and the replicated selection, ONE kernel does both:
+// every rank stores its record straight into slot [rank] of every peer's exchange block (P2P stores over
+// NVLink / NVSwitch; the blocks are cudaIpc-mapped), publishes a sequence number per peer, waits until its
+// own block holds this tick's records of all ranks, and runs the selection. Two buffers alternate by tick
+// parity: a rank can be at most one tick ahead of another (its next selection needs everyone's next
+// record), so a slot is never overwritten before its reader is done.
+constexpr int kP2pMaxWorld = 16;
+struct P2pExchange {
+  unsigned char *peers[kP2pMaxWorld];  // every rank's exchange block as mapped into this process (own block included)
+  int rank, world;
+  unsigned long long seq;              // this tick's sequence number (> 0, the same on every rank)
+  size_t stride;                       // bytes per record slot
+};
+__host__ __device__ inline size_t p2p_slot_stride() { return (argmin_record_bytes(kMaxObstacles) + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t p2p_flags_offset() { return 2 * (size_t)kP2pMaxWorld * p2p_slot_stride(); }
+__host__ __device__ inline size_t p2p_block_bytes() { return p2p_flags_offset() + 2 * kP2pMaxWorld * sizeof(unsigned long long); }
+
+// out_status: 0 ok, 1 a peer's record never arrived (bounded wait)
+__global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *local_rec, const P2pExchange X, int n_obs,
+                                                         DeviceBest *best, double *best_random, EvalResult *out,
+                                                         HostOut *host, unsigned long long ticket, int *out_status) {
+  __shared__ int s_fail;
+  const int parity = (int)(X.seq & 1ull);
+  const size_t bytes = argmin_record_bytes(n_obs);
+  const size_t slot = ((size_t)parity * kP2pMaxWorld + X.rank) * X.stride;
+  // 1. this rank's record into every rank's block (16-byte stores; the record is 8-byte aligned, sizes are multiples of 8)
+  for (int r = 0; r < X.world; ++r) {
+    double *dst = reinterpret_cast<double *>(X.peers[r] + slot);
+    const double *src = reinterpret_cast<const double *>(local_rec);
+    for (size_t i = threadIdx.x; i < bytes / sizeof(double); i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish
+  if (threadIdx.x < X.world) {
+    volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(X.peers[threadIdx.x] + p2p_flags_offset()) +
+                                        parity * kP2pMaxWorld + X.rank;
+    *flag = X.seq;
+  }
+  // 3. wait for everyone's record of this tick in the own block
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  if (threadIdx.x < X.world) {
+    volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(X.peers[X.rank] + p2p_flags_offset()) +
+                                        parity * kP2pMaxWorld + threadIdx.x;
+    unsigned long long spins = 0;
+    while (*flag != X.seq) {
+      if (++spins > (1ull << 27)) {  // ~ a second: a peer is gone; give up instead of hanging the GPU
+        s_fail = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (s_fail) {
+    if (threadIdx.x == 0) {
+      *out_status = 1;
+      if (host) host->seq[0] = ticket;  // wake the host; it reads out_status
+    }
+    return;
+  }
+  // 4. replicated selection over the own block
+  select_over_records(X.peers[X.rank] + (size_t)parity * kP2pMaxWorld * X.stride, X.stride, X.world, n_obs, best, best_random, out);
+  __syncthreads();
+  if (threadIdx.x == 0 && host) {
+    host->eval.best_index = out->best_index, host->eval.argmin_index = out->argmin_index;
+    host->eval.incumbent_changed = out->incumbent_changed, host->eval.pad = 0;
+    host->eval.best_cost = out->best_cost, host->eval.argmin_cost = out->argmin_cost;
+    host->best.present = best->present, host->best.id = best->id, host->best.type = best->type, host->best.pad = 0;
+    __threadfence_system();
+    host->seq[0] = ticket;
   }
 }
 

@@ -41,7 +41,7 @@ class Counters(C.Structure):
 
 # every symbol include/pmaf.h declares (tests check that the library exports all of them)
 API_SYMBOLS = [
-    "pmaf_last_error", "pmaf_version", "pmaf_create", "pmaf_destroy", "pmaf_set_shard", "pmaf_nccl_unique_id", "pmaf_nccl_init", "pmaf_set_nccl_comm",
+    "pmaf_last_error", "pmaf_version", "pmaf_create", "pmaf_destroy", "pmaf_set_shard", "pmaf_nccl_unique_id", "pmaf_nccl_init", "pmaf_set_nccl_comm", "pmaf_p2p_export", "pmaf_p2p_import",
     "pmaf_init", "pmaf_seed_random_vecs", "pmaf_set_random_vecs", "pmaf_get_random_vecs",
     "pmaf_set_initial_position", "pmaf_set_real_position", "pmaf_start_prediction", "pmaf_stop_prediction",
     "pmaf_evaluate_agents", "pmaf_move_real_agent", "pmaf_reset_agents", "pmaf_tick", "pmaf_get_num_agents",
@@ -86,6 +86,8 @@ def load_library():
     lib.pmaf_set_nccl_comm.argtypes = [H, C.c_void_p]
     lib.pmaf_nccl_unique_id.argtypes = [C.c_char_p]
     lib.pmaf_nccl_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
+    lib.pmaf_p2p_export.argtypes = [H, C.c_char_p]
+    lib.pmaf_p2p_import.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     lib.pmaf_init.argtypes = [H, _dp, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                               _dp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_double]
     lib.pmaf_seed_random_vecs.argtypes = [H, C.c_uint64]

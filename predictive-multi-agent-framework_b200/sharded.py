@@ -96,7 +96,7 @@ class ShardedCfManager(CfManager):
     """CfManager whose agents are one rank's block of a population sharded over `world` GPUs.
     Same call surface; per-agent getters return the LOCAL block, evaluate/tick return GLOBAL indices."""
 
-    def __init__(self, device, rank, world, group=None, **tuning):
+    def __init__(self, device, rank, world, group=None, p2p=True, **tuning):
         super().__init__(device, **tuning)
         self.rank, self.world = int(rank), int(world)
 
@@ -107,6 +107,30 @@ class ShardedCfManager(CfManager):
 
         ident = exchange_nccl_id(make_id, self.rank, group=group)
         self._check(self.lib.pmaf_nccl_init(self.h, ident, self.rank, self.world))
+        self.exchange = "nccl"
+        if p2p and self.world <= 16:
+            self._try_p2p(group)
+
+    def _try_p2p(self, group):
+        """Peer-memory exchange (pmaf_p2p_export / pmaf_p2p_import): every rank's cudaIpc handle goes to every
+        rank over torch.distributed; all ranks switch to it or all stay on NCCL."""
+        import torch.distributed as dist
+
+        buf = C.create_string_buffer(64)
+        ok = self.lib.pmaf_p2p_export(self.h, buf) == 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, buf.raw), group=group)
+        if ok and all(g[0] for g in gathered):
+            handles = b"".join(g[1] for g in gathered)
+            ok = self.lib.pmaf_p2p_import(self.h, handles, self.rank, self.world) == 0
+        else:
+            ok = False
+        agreed = [None] * self.world
+        dist.all_gather_object(agreed, ok, group=group)
+        if all(agreed):
+            self.exchange = "p2p"
+        elif ok:  # someone could not map a peer: everybody back to NCCL
+            self._check(self.lib.pmaf_p2p_export(self.h, buf))  # re-export drops the imported mappings
 
     def init(self, goal, delta_t, obs_pos, obs_vel, obs_rad, k_attr, *args, **kw):
         n_global = max(len(np.atleast_1d(k_attr)), 1)

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, p2p=True):
     import sys
 
     sys.path.insert(0, ROOT)
@@ -34,7 +34,7 @@ def _worker(rank, world, port, name, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         case = cases.all_cases()[name]
-        mgr = sharded.ShardedCfManager(rank, rank, world)
+        mgr = sharded.ShardedCfManager(rank, rank, world, p2p=p2p)
         got = case(mgr)
         want = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
         first, end = sharded.shard_range(case.scenario.num_agents, rank, world)
@@ -57,6 +57,8 @@ def _worker(rank, world, port, name, q):
         c = mgr.counters()
         if c["collectives"] < len(want["best"]):
             errs.append(f"collectives={c['collectives']}")
+        if mgr.exchange != ("p2p" if p2p else "nccl"):
+            errs.append(f"exchange={mgr.exchange}")
         q.put((rank, errs))
         mgr.close()
     except Exception as e:  # pragma: no cover
@@ -67,8 +69,11 @@ def _worker(rank, world, port, name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["near326_switching", "near326_reinit_random_incumbent", "rand5_many_agents", "moving1"])
-def test_sharded_equals_unsharded_reference(name):
+@pytest.mark.parametrize("name,p2p", [("near326_switching", True), ("near326_reinit_random_incumbent", True),
+                                      ("rand5_many_agents", True), ("moving1", True), ("near326_switching", False)])
+def test_sharded_equals_unsharded_reference(name, p2p):
+    """p2p: best-agent exchange by P2P stores into the peers' cudaIpc-mapped blocks (one fused kernel);
+    otherwise the NCCL all-gather."""
     import torch
     import torch.multiprocessing as mp
 
@@ -78,7 +83,7 @@ def test_sharded_equals_unsharded_reference(name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
