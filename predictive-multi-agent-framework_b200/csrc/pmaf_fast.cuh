@@ -263,8 +263,14 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     const unsigned lt_mask = (1u << g.lane) - 1u;
     const unsigned contrib = g.ballot(contributes);
     const int n_contrib = __popc(contrib);
-    if (contributes) st3(fbuf + 3 * __popc(contrib & lt_mask), f);
-    if (g.gl < kFastSumUnroll) st3(fbuf + 3 * (n_contrib + g.gl), mk3(0.0, 0.0, 0.0));
+    // staging as three component arrays of kFbufSlots doubles (x | y | z): two slots per 16-byte shared load
+    constexpr int kFbufSlots = 32 + kFastSumUnroll;
+    double *fx = fbuf, *fy = fbuf + kFbufSlots, *fz = fbuf + 2 * kFbufSlots;
+    if (contributes) {
+      const int rk = __popc(contrib & lt_mask);
+      fx[rk] = f.x, fy[rk] = f.y, fz[rk] = f.z;
+    }
+    if (g.gl < kFastSumUnroll) fx[n_contrib + g.gl] = 0.0, fy[n_contrib + g.gl] = 0.0, fz[n_contrib + g.gl] = 0.0;
     // reductions (exact: minima of non-negative doubles)
     min_d = g.min_reduce_nonneg(counts ? d : (double)INFINITY);
     const double mc = g.min_reduce_nonneg(close ? d : (double)INFINITY);
@@ -275,14 +281,23 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
     latch = g.ballot(first_seen) != 0u;
     latch_mine = first_seen, latch_i = i, latch_rot = rot_i;
     g.sync();
+    const double2 *fx2 = reinterpret_cast<const double2 *>(fx), *fy2 = reinterpret_cast<const double2 *>(fy),
+                  *fz2 = reinterpret_cast<const double2 *>(fz);
 #pragma unroll
-    for (int j = 0; j < kFastSumUnroll; ++j) force = add3(force, ld3(fbuf + 3 * j));
+    for (int j = 0; j < kFastSumUnroll / 2; ++j) {
+      const double2 x = fx2[j], y = fy2[j], z = fz2[j];
+      force = add3(add3(force, mk3(x.x, y.x, z.x)), mk3(x.y, y.y, z.y));
+    }
     if (n_contrib > kFastSumUnroll) {  // second block, zero-padded as well
 #pragma unroll
-      for (int j = kFastSumUnroll; j < 2 * kFastSumUnroll; ++j) force = add3(force, ld3(fbuf + 3 * j));
-      for (int j = 2 * kFastSumUnroll; j < n_contrib; j += 4) {
-        const v3 a0 = ld3(fbuf + 3 * j), a1 = ld3(fbuf + 3 * j + 3), a2 = ld3(fbuf + 3 * j + 6), a3 = ld3(fbuf + 3 * j + 9);
-        force = add3(add3(add3(add3(force, a0), a1), a2), a3);
+      for (int j = kFastSumUnroll / 2; j < kFastSumUnroll; ++j) {
+        const double2 x = fx2[j], y = fy2[j], z = fz2[j];
+        force = add3(add3(force, mk3(x.x, y.x, z.x)), mk3(x.y, y.y, z.y));
+      }
+      for (int j = kFastSumUnroll; 2 * j < n_contrib; j += 2) {
+        const double2 x0 = fx2[j], y0 = fy2[j], z0 = fz2[j], x1 = fx2[j + 1], y1 = fy2[j + 1], z1 = fz2[j + 1];
+        force = add3(add3(force, mk3(x0.x, y0.x, z0.x)), mk3(x0.y, y0.y, z0.y));
+        force = add3(add3(force, mk3(x1.x, y1.x, z1.x)), mk3(x1.y, y1.y, z1.y));
       }
     }
     g.sync();
