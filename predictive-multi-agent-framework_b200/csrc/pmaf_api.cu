@@ -1499,15 +1499,18 @@ __global__ void math_selftest_kernel(unsigned long long seed, int iters, unsigne
                __double_as_longlong(got.z) != __double_as_longlong(num.z / b))
         ++bad_div3;
     }
-    {  // fused root + reciprocal of the root (normalisations of the straight-line step)
+    {  // fused root + reciprocal of the root: a normalisation (components bounded by the norm) and a free numerator
       FastMath fm;
       double s_, y_;
       fm.sqrt_rcp_(x, s_, y_);
-      const v3 num = mk3(b, 0.37 * a, -s_);
+      const double frac = (double)(xorshift(s) >> 11) * (1.0 / 9007199254740992.0);
+      const v3 num = mk3(frac * s_, -s_, (kind & 1) ? 0.0 : s_ * 0x1p-40 * frac);
       const v3 got = fm.quot3_(num, s_, y_);
+      const double gq = fm.quot_(a, s_, y_);
       if (fm.bad()) ++flagged;
       else {
         if (__double_as_longlong(s_) != __double_as_longlong(sqrt(x))) ++bad_sqrt;
+        if (__double_as_longlong(gq) != __double_as_longlong(a / s_)) ++bad_div;
         if (__double_as_longlong(got.x) != __double_as_longlong(num.x / s_) ||
             __double_as_longlong(got.y) != __double_as_longlong(num.y / s_) ||
             __double_as_longlong(got.z) != __double_as_longlong(num.z / s_))

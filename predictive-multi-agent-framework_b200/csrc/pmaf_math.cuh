@@ -164,23 +164,37 @@ struct FastMath {
     return fma(y, e, y);
   }
   // RN(a / b) given y ~ 1/b: product, two residual corrections (the second is Markstein's final step)
-  __device__ __forceinline__ double quot_(double a, double b, double y) {
-    need_range_or_zero(a, -600, 600);
+  __device__ __forceinline__ double quot_core_(double a, double b, double y) {
     double q = a * y;
     double r = fma(-b, q, a);
     q = fma(r, y, q);
     r = fma(-b, q, a);
     q = fma(r, y, q);
-    // b > 0, so the quotient has the numerator's sign; this also restores it on a zero numerator
-    return __hiloint2double((__double2hiint(q) & 0x7fffffff) | (__double2hiint(a) & (int)0x80000000), __double2loint(q));
+    // b > 0, so the quotient has the numerator's sign; this also restores it on a zero numerator.
+    // One LOP3 (bit select): magnitude bits of q, sign bit of a.
+    unsigned hi;
+    asm("lop3.b32 %0, %1, %2, 0x7fffffff, 0xE4;" : "=r"(hi) : "r"(__double2hiint(q)), "r"(__double2hiint(a)));
+    return __hiloint2double((int)hi, __double2loint(q));
+  }
+  __device__ __forceinline__ double quot_(double a, double b, double y) {
+    need_range_or_zero(a, -600, 600);
+    return quot_core_(a, b, y);
+  }
+  // numerator known to be bounded by the (range-checked) divisor — a component of the vector whose norm
+  // b is: only a non-zero magnitude below 2^-600 can leave the proven range (a NaN component makes the
+  // norm NaN, which the root's own check rejects)
+  __device__ __forceinline__ double quot_bounded_(double a, double b, double y) {
+    flag |= (unsigned)((fabs(a) < 0x1p-600) & (a != 0.0));
+    return quot_core_(a, b, y);
   }
   __device__ __forceinline__ double div_(double a, double b) { return quot_(a, b, rcp_(b)); }
   __device__ __forceinline__ v3 div3_(v3 a, double b) {
     const double y = rcp_(b);
     return mk3(quot_(a.x, b, y), quot_(a.y, b, y), quot_(a.z, b, y));
   }
+  // a / |a| given b = |a| and y ~ 1/b (normalisations)
   __device__ __forceinline__ v3 quot3_(v3 a, double b, double y) {
-    return mk3(quot_(a.x, b, y), quot_(a.y, b, y), quot_(a.z, b, y));
+    return mk3(quot_bounded_(a.x, b, y), quot_bounded_(a.y, b, y), quot_bounded_(a.z, b, y));
   }
   // s = RN(sqrt(x)) and y ~ 1/s to within an ulp for x in [2^-600, 2^600): the Goldschmidt iteration of
   // sqrt_ already carries h ~ 1/(2 sqrt(x)), so the reciprocal of the root costs one Newton step on 2h
