@@ -110,6 +110,7 @@ struct pmaf_planner {
   DevBuf<unsigned char> xchg;          // this rank's exchange block
   unsigned char *peer_xchg[kP2pMaxWorld] = {};
   bool p2p_ready = false;
+  int p2p_rank = -1, p2p_world = 0;
   unsigned long long xseq = 0;
   DevBuf<unsigned long long> step_counter;
   DevBuf<HostOut> d_out;  // eval, best, real, real_path_out, step_counter are views into it
@@ -418,6 +419,7 @@ extern "C" int pmaf_p2p_import(pmaf_planner *p, const unsigned char *handles, in
   }
   p->h_out->p2p_fail = 0;
   p->xseq = 0;
+  p->p2p_rank = rank, p->p2p_world = world;
   p->p2p_ready = true;
   return 0;
 }
@@ -882,6 +884,9 @@ static int launch_evaluate(pmaf_planner *p, const CostParams &C) {
                       p->eval.p, 0, (HostOut *)nullptr, 0ull))
     return rc;
   if (p->p2p_ready) {  // ONE kernel: P2P stores into every peer's block over NVLink, wait, select, publish to the host
+    REQUIRE(p->p2p_rank == p->rank && p->p2p_world == p->world, PMAF_ERR_STATE,
+            "peer-memory exchange was set up for rank %d of %d, the shard is rank %d of %d", p->p2p_rank, p->p2p_world,
+            p->rank, p->world);
     P2pExchange X{};
     for (int r = 0; r < p->world; ++r) X.peers[r] = p->peer_xchg[r];
     X.rank = p->rank, X.world = p->world, X.seq = ++p->xseq, X.stride = p2p_slot_stride();

@@ -9,11 +9,14 @@
 // does overlap independent FP64 work when it is given any (tools/ubench_ilp.cu: 8.8 -> 2.4 cycles per DFMA
 // with 1 -> 8 independent chains).
 //
-// fast_step evaluates the COMMON case of a step (cf_agent.cpp:312-326) as two basic blocks with
-// selects instead of branches and no memory side effects. Everything uncommon raises `rare`:
-//   first detection of an obstacle (rotation vector latch), more than 32 broad-phase candidates, an
-//   operand outside FastMath's proven range, a norm within 1e-15 of a threshold, the sentinel within
-//   its shell, the acceleration clamp, non-unit mass, exp() outside its main path.
+// fast_step evaluates the COMMON case of a step (cf_agent.cpp:312-326) as a few large basic blocks with
+// selects instead of branches and no memory side effects until its end:
+//   * one entry branch: the step is on, the gate is open, 1..32 broad-phase candidates, unit mass
+//     (a closed gate takes the general step, which is short then);
+//   * first detections latch in place (RANDOM / GOAL / VEL by selects; HAD and the obstacle heuristics in
+//     a cold, group-uniform block), the acceleration clamp is a uniform branch;
+//   * everything else uncommon raises `rare`: an operand outside FastMath's proven range, a norm within
+//     1e-15 of a threshold, the sentinel within its shell, exp() outside its main path.
 // A rare step returns false before anything is committed and the caller runs the general step from
 // the same state. The arithmetic (operation order, roundings) is the general step's, which is the
 // reference's; tests/test_gpu_parity.py compares whole rollouts bit for bit either way.
