@@ -194,6 +194,24 @@ PMAF_HDT void agent_step(const G &g, const StepEnv &P, const SmemObstacles &obs,
   PMAF_T(6);
 }
 
+// predictObstacles (:270-276) for the CTA's shared obstacle image: exact positions by repeated addition of
+// vel * dt, and the broad-phase centres refreshed from them
+__device__ __forceinline__ void advance_obstacles(unsigned char *img, const ObstacleImage &im, int n_obs,
+                                                  const SmemObstacles &obs, const float4 *bp) {
+  double *px = const_cast<double *>(obs.px), *py = const_cast<double *>(obs.py), *pz = const_cast<double *>(obs.pz);
+  const double *dx = reinterpret_cast<const double *>(img + im.off_dx);
+  const double *dy = reinterpret_cast<const double *>(img + im.off_dy);
+  const double *dz = reinterpret_cast<const double *>(img + im.off_dz);
+  float4 *bpw = const_cast<float4 *>(bp);
+  for (int i = threadIdx.x; i < n_obs; i += blockDim.x) {
+    const double x = px[i] + dx[i], y = py[i] + dy[i], z = pz[i] + dz[i];
+    px[i] = x, py[i] = y, pz[i] = z;
+    float4 b = bpw[i];
+    b.x = (float)x, b.y = (float)y, b.z = (float)z;
+    bpw[i] = b;
+  }
+}
+
 // Rollout of every agent to termination. Each group continues ITS agent from the agent's current
 // state (latest path point, velocity, min_obs_dist, known flags, path length, workspace cost) —
 // which resetEEAgents made uniform in the normal tick order — so any call order of the reference
@@ -358,6 +376,55 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         pending = true;
       }
     }
+  } else if constexpr (FAST && DYNAMIC) {
+    // The same rotated loop for moving obstacles: the CTA's warps step in lockstep around the shared
+    // obstacle image (a finished agent's warp keeps taking part in the barriers).
+    v3 prev = p;
+    bool pending = false;
+    for (;;) {
+      if (alive) {
+        const v3 seg = sub3(p, prev);
+        const double zs = dot3(seg, seg);
+        const v3 goal_vec = sub3(goal, p);
+        bool pr_bad;
+        const bool had_step = pending;  // the previous iteration took a step: commit it now
+        Prologue pr = step_prologue_nofallback<false>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, had_step, k, pr_bad);
+        const StepNorms &sn = pr.sn;
+        const double path_len_before = path_len;
+        path_len += sn.seg_len;
+        if (fused) {
+          const double w = add_workspace_cost_bf(ws_cost, p, wsp.ws, wsp.k_workspace);
+          ws_cost = had_step ? w : ws_cost;
+        }
+        st3_if(path_row + (size_t)n_path * 3, p, had_step & (g.gl == 0));
+        n_path += had_step ? 1 : 0, steps_run += had_step ? 1 : 0;
+        pending = false;
+        bool step_on = (sn.dist_goal > 0.1) & (n_path < max_steps) & !pr_bad;  // :310-311
+        prev = p;
+        const bool done = fast_step<false>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
+                                           goal_vec, pr, p, v, min_obs, nullptr, step_on);
+        if (!done) {
+          if (pr_bad) {
+            redo_prologue_exact<false>(pr, goal_vec, v, zs, had_step, k);
+            path_len = path_len_before + sn.seg_len;
+            step_on = sn.dist_goal > 0.1 && n_path < max_steps;
+          }
+          if (step_on) {
+            ++general_steps;
+            agent_step<false, true>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec,
+                                    pr, p, v, min_obs PMAF_T_PASS);
+            pending = true;
+          } else {
+            alive = false;
+          }
+        } else {
+          pending = true;
+        }
+      }
+      if (!__syncthreads_or(alive)) break;
+      advance_obstacles(img, P.img, env.n_obs, obs, bp);
+      __syncthreads();
+    }
   } else
   if (DYNAMIC || alive)  // static scenes: an agent's warp leaves the loop directly when its rollout ends
   for (;;) {
@@ -416,19 +483,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
       // predictObstacles (:270-276): every private obstacle copy advances identically, so the CTA
       // keeps ONE copy and steps it in lockstep with its agents
       if (!__syncthreads_or(alive)) break;
-      double *px = const_cast<double *>(obs.px), *py = const_cast<double *>(obs.py),
-             *pz = const_cast<double *>(obs.pz);
-      const double *dx = reinterpret_cast<const double *>(img + P.img.off_dx);
-      const double *dy = reinterpret_cast<const double *>(img + P.img.off_dy);
-      const double *dz = reinterpret_cast<const double *>(img + P.img.off_dz);
-      float4 *bpw = const_cast<float4 *>(bp);
-      for (int i = threadIdx.x; i < env.n_obs; i += blockDim.x) {
-        const double x = px[i] + dx[i], y = py[i] + dy[i], z = pz[i] + dz[i];
-        px[i] = x, py[i] = y, pz[i] = z;
-        float4 b = bpw[i];
-        b.x = (float)x, b.y = (float)y, b.z = (float)z;
-        bpw[i] = b;
-      }
+      advance_obstacles(img, P.img, env.n_obs, obs, bp);
       __syncthreads();
     }
   }
