@@ -795,12 +795,18 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
   // many warps per SM: the 128-register build keeps 16 warps resident; few: the 255-register build
   int occ = p->tune_occ;
   // measured on B200: the 255-register latency build wins up to ~8 warps per SM (C5: 1024 agents), the
-  // 170-register build beyond (C3: 4096, C4 shard: 8192 agents)
-  if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 12 * 148) ? 3 : 1;
+  // 170-register build beyond (C3: 4096, C4 shard: 8192 agents) — unless the scene is static with more than
+  // 64 field obstacles, where the latency build's chunked straight-line step (MULTI) is used
+  const bool multi_ok = LPA == 32 && !dynamic && p->O - 1 > kBroadUnrolledRounds * 32 && block <= 256;
+  if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 12 * 148 && !multi_ok) ? 3 : 1;
   if (LPA < 16 || block > 128) occ = 1;  // the occupancy builds exist for 16/32 lanes per agent, CTAs <= 128 threads
   auto kern = dynamic ? rollout_kernel<LPA, true, 1> : rollout_kernel<LPA, false, 1>;
+  if constexpr (LPA == 32) {
+    if (occ == 1 && multi_ok) kern = rollout_kernel<32, false, 1, true>;
+  }
   if constexpr (LPA >= 16) {
     if (occ == 3) kern = dynamic ? rollout_kernel<LPA, true, 3> : rollout_kernel<LPA, false, 3>;
+
     if (occ == 4) kern = dynamic ? rollout_kernel<LPA, true, 4> : rollout_kernel<LPA, false, 4>;
   }
   p->ctr.occupancy_build = occ;

@@ -351,6 +351,224 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
   return true;
 #undef PMAF_RARE
 }
+
+// The same step for obstacle sets whose candidates do not fit one lane each (more than 64 field
+// obstacles: the broad phase is a loop, the narrow phase runs in chunks of 32 candidates). Per chunk the
+// straight-line narrow phase of fast_step; contributions are summed chunk after chunk (candidate order =
+// obstacle order), the per-lane running minima are reduced once after the last chunk, and
+// attractorForceScaling's tail is evaluated once for the winner (these populations run several warps per
+// scheduler: fewer instructions beat a shorter dependency chain). First detections are committed chunk by
+// chunk: a later rare event re-runs the general step, which then finds the obstacle known with exactly the
+// rotation vector it would have latched itself.
+template <bool STATIC_VEL>
+__device__ __forceinline__ bool fast_step_multi(const Group<32> &g, const StepEnv &P, const SmemObstacles &obs,
+                                                const uint16_t *cand, double *fbuf, const KnownBits &known, int type,
+                                                const AgentConsts &c, const FastConsts &fc, v3 init_pos, double *rot_row,
+                                                const double *random_row, v3 goal_vec, const Prologue &pr, v3 &p,
+                                                v3 &v, double &min_obs, bool step_on, const uint16_t *nn_table) {
+  const StepNorms &sn = pr.sn;
+  const int n_cand = pr.n_cand;
+  bool rare = false;
+  const v3 d0 = sub3(p, init_pos);
+  const double z0 = dot3(d0, d0);
+  const bool near_start = z0 < fc.thr_start.lo;
+  const bool start_ambiguous = !near_start & !(z0 > fc.thr_start.hi);
+  const bool gate_open = !(sn.dist_goal < c.approach_dist) & !((sn.vn < c.half_vmax) & near_start);
+  if (!(step_on & fc.usable & (n_cand > 0) & gate_open & !start_ambiguous)) return false;
+  const v3 dvs = sub3(p, obs.pos(P.n_obs - 1));
+  rare |= !(dot3(dvs, dvs) > c.repel_far2);
+
+  v3 force = mk3(0.0, 0.0, 0.0);
+  double lmin = (double)INFINITY, lcd = (double)INFINITY;  // per-lane running minima over the chunks
+  int lci = 0x7fffffff;                                    // candidate position of the lane's closest obstacle
+  const unsigned lt_mask = (1u << g.lane) - 1u;
+  const bool uses_rot = (fc.tbits & kTUsesRot) != 0;
+  constexpr int kFbufSlots = 32 + kFastSumUnroll;
+  double *fx = fbuf, *fy = fbuf + kFbufSlots, *fz = fbuf + 2 * kFbufSlots;
+  const double2 *fx2 = reinterpret_cast<const double2 *>(fx), *fy2 = reinterpret_cast<const double2 *>(fy),
+                *fz2 = reinterpret_cast<const double2 *>(fz);
+  g.sync();  // cand[] was written by the broad phase
+  for (int c0 = 0; c0 < n_cand; c0 += 32) {
+    const int ci = c0 + g.gl;
+    const bool active = ci < n_cand;
+    const int i = (int)cand[active ? ci : 0];
+    const v3 oi = obs.pos(i);
+    const double rs = obs.rsum(i);
+    const bool is_known = known.test(i);
+    v3 rot_i = mk3(0.0, 0.0, 1.0);
+    if (uses_rot & is_known) rot_i = ld3(rot_row + 3 * i);
+    const v3 rov = sub3(oi, p);
+    const v3 rel = STATIC_VEL ? v : sub3(v, obs.vel(i));
+    FastMath fa, fb;
+    const double z = dot3(rov, rov);
+    double n, yn;
+    fa.sqrt_rcp_(z, n, yn);
+    const v3 to_obs = fa.quot3_(rov, n, yn);
+    const double d = clamp_dist(n - rs);
+    const bool skip = (dot3(to_obs, pr.ghat) < -0.01) & (dot3(rov, rel) < -0.01);  // :79-82
+    const bool counts = active & !skip;
+    const bool close = active & (d < c.shell);
+    const bool in_shell = close & !skip;
+    const bool first_seen = in_shell & !is_known;
+    bool latch_flag = false;
+    if (first_seen & ((fc.tbits & kTRandom) != 0)) rot_i = cross3(pr.ghat, ld3(random_row + 3 * i));
+    if ((fc.tbits & (kTUsesRot | kTRandom)) == kTUsesRot) {
+      unsigned todo = g.ballot(first_seen);
+      if (__builtin_expect(todo != 0u, 0)) {  // cold: see fast_step
+        FastMath fscan, frot;
+        int nn = 0;
+        if ((fc.tbits & kTNeedsNN) && nn_table) {
+          nn = nn_table[i];
+        } else if (fc.tbits & kTNeedsNN) {
+          const int n_field = P.n_obs - 1;
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int id = g.bcast(i, src);
+            const v3 o_id = obs.pos(id);
+            double best = 100.0;
+            int best_i = 0x7fffffff;
+            for (int k = g.gl; k < n_field; k += 32) {
+              const v3 dk = sub3(o_id, obs.pos(k));
+              const double dist = fscan.sqrt_(k != id ? dot3(dk, dk) : 1.0);
+              if ((k != id) & (best > dist)) best = dist, best_i = k;
+            }
+            g.argmin_reduce_nonneg(best, best_i);
+            if (g.lane == src) nn = best_i == 0x7fffffff ? 0 : best_i;
+          }
+        }
+        v3 r;
+        if (type == HAD_HEURISTIC) {
+          const double sh = frot.div_(dot3(rov, goal_vec), sn.dist_goal * sn.dist_goal);
+          const v3 dh = sub3(add3(p, mul3(goal_vec, sh)), oi);
+          const v3 ch = cross3(dh, goal_vec);
+          double nh, yh;
+          frot.sqrt_rcp_(dot3(ch, ch), nh, yh);
+          r = frot.quot3_(ch, nh, yh);
+        } else {
+          const v3 obstacle_vec = sub3(obs.pos(nn), oi);
+          const v3 obst_current = sub3(mul3(to_obs, dot3(obstacle_vec, to_obs)), obstacle_vec);
+          v3 cur = obst_current;
+          if (type == GOAL_OBSTACLE_HEURISTIC) {
+            const v3 goal_current = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+            double n1, y1, n2, y2, n3, y3;
+            frot.sqrt_rcp_(dot3(goal_current, goal_current), n1, y1);
+            frot.sqrt_rcp_(dot3(obst_current, obst_current), n2, y2);
+            cur = add3(frot.quot3_(goal_current, n1, y1), frot.quot3_(obst_current, n2, y2));
+            FastMath fsum;
+            fsum.sqrt_rcp_(dot3(cur, cur), n3, y3);
+            const v3 q3 = fsum.quot3_(cur, n3, y3);
+            const bool tiny = n3 < 1e-10;
+            frot.flag |= (fsum.bad() && !(dot3(cur, cur) == 0.0)) ? 1u : 0u;
+            cur = (tiny | (dot3(cur, cur) == 0.0)) ? mk3(0.0, 0.0, 1.0) : q3;
+          }
+          const v3 cr = cross3(cur, to_obs);
+          double nr, yr;
+          frot.sqrt_rcp_(dot3(cr, cr), nr, yr);
+          r = frot.quot3_(cr, nr, yr);
+        }
+        if (first_seen) rot_i = r;
+        latch_flag = fscan.bad() | (first_seen & frot.bad());
+      }
+    }
+    double zr, vel_norm;
+    v3 nv;
+    if (STATIC_VEL) {
+      zr = sn.zv, vel_norm = sn.vn, nv = pr.nv_static;
+    } else {
+      double yv;
+      zr = dot3(rel, rel);
+      fb.sqrt_rcp_(zr, vel_norm, yv);
+      nv = fb.quot3_(rel, vel_norm, yv);
+    }
+    const v3 nv_eigen = zr > 0.0 ? nv : rel;
+    v3 cin = cross3(to_obs, rot_i);
+    if (fc.tbits & kTGoal) cin = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+    if (fc.tbits & kTVel) cin = sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs)));
+    double nc, yc;
+    fb.sqrt_rcp_(dot3(cin, cin), nc, yc);
+    v3 current = fb.quot3_(cin, nc, yc);
+    if (!uses_rot & (nc < 1e-10)) current = mk3(0.0, 0.0, 1.0);
+    const v3 f = mul3(cross3(nv, cross3(current, nv)), fb.div_(c.k_circ, d * d));
+    const bool contributes = in_shell & (vel_norm != 0);
+    const bool lane_bad = latch_flag | (active & (fa.bad() | (close & fb.bad())));
+    // running minima (strict <: the first of equals within a lane has the lower obstacle index)
+    if (counts & (d < lmin)) lmin = d;
+    if (close & (d < lcd)) lcd = d, lci = ci;
+    // ordered sum of this chunk's contributions
+    const unsigned contrib = g.ballot(contributes);
+    const int n_contrib = __popc(contrib);
+    if (contributes) {
+      const int rk = __popc(contrib & lt_mask);
+      fx[rk] = f.x, fy[rk] = f.y, fz[rk] = f.z;
+    }
+    if (g.gl < kFastSumUnroll) fx[n_contrib + g.gl] = 0.0, fy[n_contrib + g.gl] = 0.0, fz[n_contrib + g.gl] = 0.0;
+    const bool any_bad = g.ballot(lane_bad) != 0u;
+    rare |= any_bad;
+    // first detections of this chunk (:93-95); not while an operand was out of range
+    if (__builtin_expect(g.ballot(first_seen) != 0u, 0)) {
+      if (first_seen & !any_bad) {
+        st3(rot_row + 3 * i, rot_i);
+        known.set(i);
+      }
+    }
+    g.sync();
+#pragma unroll
+    for (int j = 0; j < kFastSumUnroll / 2; ++j) {
+      const double2 x = fx2[j], y = fy2[j], z2 = fz2[j];
+      force = add3(add3(force, mk3(x.x, y.x, z2.x)), mk3(x.y, y.y, z2.y));
+    }
+    if (n_contrib > kFastSumUnroll) {
+      for (int j = kFastSumUnroll / 2; 2 * j < n_contrib; j += 2) {
+        const double2 x0 = fx2[j], y0 = fy2[j], z0 = fz2[j], x1 = fx2[j + 1], y1 = fy2[j + 1], z1 = fz2[j + 1];
+        force = add3(add3(force, mk3(x0.x, y0.x, z0.x)), mk3(x0.y, y0.y, z0.y));
+        force = add3(add3(force, mk3(x1.x, y1.x, z1.x)), mk3(x1.y, y1.y, z1.y));
+      }
+    }
+    g.sync();
+  }
+  // reductions over the lanes' running minima
+  const double min_d = g.min_reduce_nonneg(lmin);
+  const bool has_closest = g.ballot(lci != 0x7fffffff) != 0u;
+  double kgs_closest = 1.0;
+  FastMath fm;
+  if (has_closest) {  // attractorForceScaling's tail (:212-226) once, for the first obstacle with the smallest distance
+    g.argmin_reduce_nonneg(lcd, lci);
+    const v3 o_c = obs.pos((int)cand[lci]);
+    kgs_closest = attractor_scaling(fm, goal_vec, sn.dist_goal, p, v, sn.vn, c, lcd, o_c);
+  }
+  // ---- scalar rest of the step (as in fast_step) ----
+  const double new_min_obs = min_d < min_obs ? min_d : min_obs;
+  const double fzz = dot3(force, force);
+  const bool big = fzz > fc.thr_force.hi;
+  rare |= !big & !(fzz < fc.thr_force.lo);
+  const double k_goal_scale = (has_closest & big) ? kgs_closest : 1.0;
+  force = add3(force, mk3(0.0, 0.0, 0.0));
+  const v3 fa3 = add3(force, mul3(sub3(sn.vel_des, v), k_goal_scale * c.k_damp));
+  if (c.k_attr != 0.0) force = fa3;
+  {
+    const double zacc = dot3(force, force);
+    const bool clamp = zacc > fc.thr_acc.hi;
+    rare |= !clamp & !(zacc < fc.thr_acc.lo);
+    if (clamp) {
+      double na, ya;
+      fm.sqrt_rcp_(zacc, na, ya);
+      force = mul3(force, fm.quot_(13.0, na, ya));
+    }
+  }
+  const double dt = P.pred_dt;
+  const v3 np = mk3((p.x + 0.5 * force.x * dt * dt) + v.x * dt, (p.y + 0.5 * force.y * dt * dt) + v.y * dt,
+                    (p.z + 0.5 * force.z * dt * dt) + v.z * dt);
+  v3 nvel = add3(v, mul3(force, dt));
+  double vel_norm, yvn;
+  fm.sqrt_rcp_(dot3(nvel, nvel), vel_norm, yvn);
+  const double scale = fm.quot_(c.vel_max, vel_norm, yvn);
+  if (vel_norm > c.vel_max) nvel = mul3(nvel, scale);
+  rare |= fm.bad();
+  if (__builtin_expect(rare, 0)) return false;
+  p = np, v = nvel, min_obs = new_min_obs;
+  return true;
+}
 #endif  // __CUDACC__
 
 }  // namespace pmaf

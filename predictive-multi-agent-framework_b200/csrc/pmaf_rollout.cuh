@@ -118,16 +118,19 @@ PMAF_HDT Prologue step_prologue(const G &g, const float4 *bp, int n_field, uint1
 // The same without the in-place fallback (rotated loop of the latency build): an operand outside FastMath's
 // range only raises `bad`; the caller re-evaluates with redo_prologue_exact on its slow path, so the hot
 // block carries no reconvergence region.
-template <bool STATIC_VEL, class G>
+template <bool STATIC_VEL, bool BROAD = true, class G>
 PMAF_HDT Prologue step_prologue_nofallback(const G &g, const float4 *bp, int n_field, uint16_t *cand, v3 goal_vec, v3 p,
                                            v3 v, double zseg, bool has_seg, const AgentConsts &c, bool &bad) {
   Prologue pr;
   FastMath fm;
   pr.sn = step_norms(fm, goal_vec, v, zseg, has_seg, c);
   step_units<STATIC_VEL>(fm, goal_vec, v, pr.sn, pr.ghat, pr.nv_static);
-  const bool small = n_field <= kBroadUnrolledRounds * G::kLanes;
-  pr.n_cand = broad_phase_unrolled<kBroadUnrolledRounds>(g, bp, small ? n_field : 0, p, cand);
-  if (!small) pr.n_cand = -1;
+  pr.n_cand = -1;
+  if (BROAD) {  // large obstacle sets (MULTI) run the broad phase as a loop afterwards
+    const bool small = n_field <= kBroadUnrolledRounds * G::kLanes;
+    pr.n_cand = broad_phase_unrolled<kBroadUnrolledRounds>(g, bp, small ? n_field : 0, p, cand);
+    if (!small) pr.n_cand = -1;
+  }
   bad = fm.bad();
   return pr;
 }
@@ -219,7 +222,9 @@ __device__ __forceinline__ void advance_obstacles(unsigned char *img, const Obst
 // OCC = resident CTAs per SM the register budget is sized for: 1 (up to 255 registers: the latency-bound
 // case, one warp per scheduler), or 3 / 4 CTAs of 128 threads (170 / 128 registers: populations that
 // fill the machine trade registers for resident warps).
-template <int LPA, bool DYNAMIC, int OCC>
+// MULTI (static latency build only): more than 64 field obstacles — broad phase as a loop, narrow phase in
+// chunks of 32 candidates (fast_step_multi).
+template <int LPA, bool DYNAMIC, int OCC, bool MULTI = false>
 __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(const PlannerDev P) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -301,6 +306,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace, rz);
   // latency build, one warp per agent: common steps take the straight-line path (pmaf_fast.cuh)
   constexpr bool FAST = OCC == 1 && LPA == 32;
+  static_assert(!MULTI || (FAST && !DYNAMIC), "MULTI exists for the static latency build only");
   if (FAST && have_agent) {  // the agent's rotation-vector row into L1 now: its first uses sit on the critical path
     const char *row = reinterpret_cast<const char *>(rot_row);
     for (int off = g.gl * 128; off < P.n_obs * 24; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + off));
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         const double zs = dot3(seg, seg);
         const v3 goal_vec = sub3(goal, p);
         bool pr_bad;
-        Prologue pr = step_prologue_nofallback<true>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k, pr_bad);
+        Prologue pr = step_prologue_nofallback<true, !MULTI>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k, pr_bad);
         const StepNorms &sn = pr.sn;
         const double path_len_before = path_len;
         path_len += sn.seg_len;  // getPathLength term (:29), in path order; 0 while nothing is pending
@@ -351,8 +357,15 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
 #else
         unsigned *why = nullptr;
 #endif
-        const bool done = fast_step<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
-                                          goal_vec, pr, p, v, min_obs, why, step_on, nn_table);
+        bool done;
+        if constexpr (MULTI) {
+          pr.n_cand = broad_phase_loop(g, bp, env.n_obs - 1, p, cand);
+          done = fast_step_multi<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec,
+                                       pr, p, v, min_obs, step_on, nn_table);
+        } else {
+          done = fast_step<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec, pr,
+                                 p, v, min_obs, why, step_on, nn_table);
+        }
         if (!done) {
           if (pr_bad) {  // an operand outside FastMath's range: the prologue again with the IEEE built-ins
             redo_prologue_exact<true>(pr, goal_vec, v, zs, pending, k);
