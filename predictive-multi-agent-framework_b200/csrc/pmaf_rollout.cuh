@@ -66,12 +66,10 @@ PMAF_HDT int broad_phase_loop(const G &g, const float4 *bp, int n_field, v3 p, u
   int n_cand = 0;
   for (int base = 0; base < n_field; base += LPA) {
     const int i = base + g.gl;
-    bool cnd = false;
-    if (i < n_field) {
-      const float4 b = bp[i];
-      const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
-      cnd = dx * dx + dy * dy + dz * dz < b.w;
-    }
+    // unconditional load of a valid record (index n_field is the sentinel's): no branch inside the loop body
+    const float4 b = bp[i < n_field ? i : n_field];
+    const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
+    const bool cnd = (i < n_field) & (dx * dx + dy * dy + dz * dz < b.w);
     const unsigned m = g.ballot(cnd);
     if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
     n_cand += PMAF_POPC(m);
