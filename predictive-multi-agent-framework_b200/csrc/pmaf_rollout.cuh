@@ -64,15 +64,20 @@ PMAF_HDT int broad_phase_loop(const G &g, const float4 *bp, int n_field, v3 p, u
   const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
   const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
   int n_cand = 0;
-  for (int base = 0; base < n_field; base += LPA) {
-    const int i = base + g.gl;
-    // unconditional load of a valid record (index n_field is the sentinel's): no branch inside the loop body
-    const float4 b = bp[i < n_field ? i : n_field];
-    const float dx = b.x - fx, dy = b.y - fy, dz = b.z - fz;
-    const bool cnd = (i < n_field) & (dx * dx + dy * dy + dz * dz < b.w);
-    const unsigned m = g.ballot(cnd);
-    if (cnd) cand[n_cand + PMAF_POPC(m & lt_mask)] = (uint16_t)i;
-    n_cand += PMAF_POPC(m);
+  // two rounds per iteration: independent loads and compares, half the loop overhead
+  for (int base = 0; base < n_field; base += 2 * LPA) {
+    const int i0 = base + g.gl, i1 = i0 + LPA;
+    // unconditional loads of valid records (index n_field is the sentinel's): no branch inside the loop body
+    const float4 b0 = bp[i0 < n_field ? i0 : n_field], b1 = bp[i1 < n_field ? i1 : n_field];
+    const float dx0 = b0.x - fx, dy0 = b0.y - fy, dz0 = b0.z - fz;
+    const float dx1 = b1.x - fx, dy1 = b1.y - fy, dz1 = b1.z - fz;
+    const bool c0 = (i0 < n_field) & (dx0 * dx0 + dy0 * dy0 + dz0 * dz0 < b0.w);
+    const bool c1 = (i1 < n_field) & (dx1 * dx1 + dy1 * dy1 + dz1 * dz1 < b1.w);
+    const unsigned m0 = g.ballot(c0), m1 = g.ballot(c1);
+    if (c0) cand[n_cand + PMAF_POPC(m0 & lt_mask)] = (uint16_t)i0;
+    n_cand += PMAF_POPC(m0);
+    if (c1) cand[n_cand + PMAF_POPC(m1 & lt_mask)] = (uint16_t)i1;
+    n_cand += PMAF_POPC(m1);
   }
   return n_cand;
 }
