@@ -64,20 +64,35 @@ PMAF_HDT int broad_phase_loop(const G &g, const float4 *bp, int n_field, v3 p, u
   const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
   const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
   int n_cand = 0;
-  // two rounds per iteration: independent loads and compares, half the loop overhead
-  for (int base = 0; base < n_field; base += 2 * LPA) {
-    const int i0 = base + g.gl, i1 = i0 + LPA;
-    // unconditional loads of valid records (index n_field is the sentinel's): no branch inside the loop body
-    const float4 b0 = bp[i0 < n_field ? i0 : n_field], b1 = bp[i1 < n_field ? i1 : n_field];
-    const float dx0 = b0.x - fx, dy0 = b0.y - fy, dz0 = b0.z - fz;
-    const float dx1 = b1.x - fx, dy1 = b1.y - fy, dz1 = b1.z - fz;
-    const bool c0 = (i0 < n_field) & (dx0 * dx0 + dy0 * dy0 + dz0 * dz0 < b0.w);
-    const bool c1 = (i1 < n_field) & (dx1 * dx1 + dy1 * dy1 + dz1 * dz1 < b1.w);
-    const unsigned m0 = g.ballot(c0), m1 = g.ballot(c1);
-    if (c0) cand[n_cand + PMAF_POPC(m0 & lt_mask)] = (uint16_t)i0;
-    n_cand += PMAF_POPC(m0);
-    if (c1) cand[n_cand + PMAF_POPC(m1 & lt_mask)] = (uint16_t)i1;
-    n_cand += PMAF_POPC(m1);
+  // four rounds per iteration: independent loads and compares, a quarter of the loop overhead
+  constexpr int R = 4;
+  for (int base = 0; base < n_field; base += R * LPA) {
+    float4 b[R];
+    bool c[R];
+    unsigned m[R];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < R; ++r) {  // unconditional loads of valid records (index n_field is the sentinel's)
+      const int i = base + r * LPA + g.gl;
+      b[r] = bp[i < n_field ? i : n_field];
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < R; ++r) {
+      const int i = base + r * LPA + g.gl;
+      const float dx = b[r].x - fx, dy = b[r].y - fy, dz = b[r].z - fz;
+      c[r] = (i < n_field) & (dx * dx + dy * dy + dz * dz < b[r].w);
+      m[r] = g.ballot(c[r]);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < R; ++r) {
+      if (c[r]) cand[n_cand + PMAF_POPC(m[r] & lt_mask)] = (uint16_t)(base + r * LPA + g.gl);
+      n_cand += PMAF_POPC(m[r]);
+    }
   }
   return n_cand;
 }
