@@ -45,7 +45,7 @@ typedef enum {
   PMAF_ERR_ARG = -1,    /* null pointer, size mismatch, index out of range */
   PMAF_ERR_STATE = -2,  /* call order: e.g. move_real_agent before any evaluate_agents */
   PMAF_ERR_CUDA = -3,   /* CUDA runtime / device error */
-  PMAF_ERR_NCCL = -4,   /* NCCL error (sharded planners only) */
+  PMAF_ERR_NCCL = -4,   /* best-agent exchange failed: NCCL error, or a peer's record never arrived (sharded planners only) */
   PMAF_ERR_ALLOC = -5
 } pmaf_status;
 
@@ -79,10 +79,11 @@ int pmaf_destroy(pmaf_planner *p);
  * (cpp:70-104). With n_global == n_local (default) the planner is unsharded. */
 int pmaf_set_shard(pmaf_planner *p, int n_global, int first_agent, int rank, int world);
 
-/* Sharded planners exchange ONE NCCL all-gather per evaluate (per control tick): every rank's
- * (min cost, argmin index, incumbent cost) record plus the random vectors of its local winner,
- * 40 + 24*n_obs bytes per rank, followed by a replicated serial selection — bit-identical to the
- * reference's serial argmin over the whole population. The communicator is either created here
+/* Sharded planners exchange ONE record per rank per evaluate (per control tick): (min cost, argmin
+ * index, incumbent cost) plus the random vectors of the rank's local winner, 40 + 24*n_obs bytes,
+ * followed by a replicated serial selection — bit-identical to the reference's serial argmin over
+ * the whole population. Transport: NVLink peer memory (pmaf_p2p_export / pmaf_p2p_import below) or
+ * an NCCL all-gather. The NCCL communicator is either created here
  * from an id made on one rank and distributed by the host (torch.distributed, MPI, ...), or
  * attached from outside (ncclComm_t as void*). libnccl.so.2 is dlopen()ed on first use. */
 int pmaf_nccl_unique_id(unsigned char id_out[128]);
