@@ -857,10 +857,11 @@ __global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *lo
   }
   __threadfence_system();
   __syncthreads();
-  // 2. publish
+  // 2. publish (the publishing thread fences again after the barrier: cumulative over the block's stores)
   if (threadIdx.x < X.world) {
     volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(X.peers[threadIdx.x] + p2p_flags_offset()) +
                                         parity * kP2pMaxWorld + X.rank;
+    __threadfence_system();
     *flag = X.seq;
   }
   // 3. wait for everyone's record of this tick in the own block
