@@ -208,7 +208,6 @@ def run_ours(args, rank, world, local_rank):
         tick()
         dev_ms += mgr.timer_stop()  # waits for the rollout this tick launched
     barrier()
-    clocks = sampler.stop() if sampler else None
     c1 = mgr.counters()
     steps_local = c1["agent_steps_total"] - c0["agent_steps_total"]
     launches = c1["kernel_launches"] - c0["kernel_launches"]
@@ -228,6 +227,7 @@ def run_ours(args, rank, world, local_rank):
                                  feed_frequency=feed.frequency, wait_rollout=True, flush_l2=True)
     e1 = mgr.counters()
     e2e_steps_local = e1["agent_steps_total"] - e0["agent_steps_total"]
+    clocks = sampler.stop() if sampler else None  # sampled over both timed regions (device-resident and e2e)
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
     n = torch.tensor([steps_local, e2e_steps_local], dtype=torch.float64, device="cuda")
