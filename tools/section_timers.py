@@ -1,5 +1,8 @@
-"""Where do the cycles of one agent-step go? Runs a workload on the instrumented build
-(libpmaf_timers.so: csrc compiled with -DPMAF_SECTION_TIMERS) and prints cycles per step and section.
+"""Where do the cycles of one agent-step of the GENERAL step go? Runs a workload on the instrumented build
+(libpmaf_timers.so: make -C .../csrc OUT=../libpmaf_timers.so EXTRA=-DPMAF_SECTION_TIMERS) and prints cycles
+per step and section. The section markers sit in agent_step / field_pass; the straight-line steps of the
+latency build (pmaf_fast.cuh) are profiled with tools/fast_stats.py and ncu instead, so only the steps that
+fall back to the general step are accounted here.
 
     python tools/section_timers.py [c2|c3|c5]
 """
