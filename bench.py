@@ -11,6 +11,11 @@ integration steps (agents x (horizon-1) on the synthetic workloads) per second.
   e2e     the five reference-facing CfManager calls per tick through the C ABI with HOST buffers
           (obstacle lists re-uploaded every call, results read back), driven by the library's C++
           host loop pmaf_dry_run (the reference's caller is a C++ node), wall clock.
+  workloads   the headline line is BASELINE.json configs[1] (C2); the same JSON line carries
+          time-boxed sub-records of the other BASELINE configs — one GPU: C3, C5 and one GPU's
+          share of C4; N GPUs: C4 with 8192 agents per GPU (N = 8 is C4 proper, 65 536 agents).
+  sharded_parity   N > 1: before anything is timed, three ticks of a golden case run sharded over
+          the N ranks and are compared bit for bit with the reference's golden vectors.
   --impl reference   the reference's own CPU implementation (oracle/_ref when built, else the
           C port) on all host threads, same workload and metric.
 """
@@ -35,6 +40,15 @@ from pmaf_b200 import loop, scenarios  # noqa: E402
 METRIC = "agent-prediction-steps/sec"
 WORKLOADS = {"c2": scenarios.c2, "c3": scenarios.c3, "c4": scenarios.c4, "c5": scenarios.c5,
              "c4s": lambda: scenarios.c4(8192)}  # c4s: one GPU's share of C4 (65536 agents over 8 GPUs)
+SUB_TICKS = 10  # timed ticks of every sub-record (plus 3 warm-up ticks)
+
+
+def host_threads():
+    """Host threads this process may run on — NOT OpenMP's default, which torchrun pins to 1 (OMP_NUM_THREADS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def workload_config(sc, n_gpus, extra=None):
@@ -50,7 +64,7 @@ def workload_config(sc, n_gpus, extra=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -60,7 +74,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -68,7 +82,7 @@ class ClockSampler:
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
@@ -85,7 +99,8 @@ class ClockSampler:
                 if v.strip().lower() == "active":
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "span": "all timed regions of this run (headline, e2e and sub-records), 50 ms period"}
 
 
 def measured_peaks():
@@ -107,7 +122,7 @@ def measured_traffic(workload):
         return None
 
 
-def cpu_planner(threads=0):
+def cpu_planner(threads):
     from oracle import cpu_planners
 
     if cpu_planners.have_ref():
@@ -119,8 +134,8 @@ def cpu_planner(threads=0):
 
 def time_cpu(sc, ticks, warmup=1):
     """Closed-loop ticks of the reference CPU path on all host threads; returns (steps/s, seconds, kind, cores)."""
-    p, kind = cpu_planner()
-    cores = p.host_threads()
+    cores = host_threads()
+    p, kind = cpu_planner(cores)
     feed = loop.ObstacleFeed(sc)
     loop.plan_begin(p, sc)
     steps = 0
@@ -143,8 +158,9 @@ def run_reference(args, rank, world):
         return
     sc = WORKLOADS[args.workload]()
     ticks = max(1, args.steps)
+    cores = host_threads()
     # bound the run: ~65 ns per (agent, step, obstacle) per core
-    est = sc.num_agents * sc.max_prediction_steps * sc.num_obstacles * 65e-9 / max(os.cpu_count() or 1, 1)
+    est = sc.num_agents * sc.max_prediction_steps * sc.num_obstacles * 65e-9 / max(cores, 1)
     budget = 120.0
     if est * (ticks + args.warmup) > budget:
         ticks = max(1, int(budget / est) - args.warmup)
@@ -160,33 +176,61 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    from pmaf_b200 import planner
+# ---- the CUDA arm -----------------------------------------------------------------------------------------------------
+class Env:
+    """Process-group plumbing of one rank (torch.distributed is used for nothing else)."""
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — libpmaf has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sc1 = WORKLOADS[args.workload]()
-    # weak scaling: every GPU owns `agents` agents of a population of agents * world
-    sc = sc1 if world == 1 else sc1.with_(num_agents=sc1.num_agents * world, name=f"{sc1.name}_x{world}")
-    if world == 1:
-        mgr = planner.CfManager(local_rank, lanes_per_agent=args.lanes, block_threads=args.block, occupancy=args.occ)
-    else:
+    def __init__(self, rank, world, local_rank):
+        import torch
+
+        self.torch, self.rank, self.world, self.local_rank = torch, rank, world, local_rank
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, maxes, sums):
+        t = self.torch.tensor(maxes, dtype=self.torch.float64, device="cuda")
+        n = self.torch.tensor(sums, dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(n, op=self.dist.ReduceOp.SUM)
+        return t.tolist(), n.tolist()
+
+    def all_ok(self, ok):
+        (worst,), _ = self.reduce([0.0 if ok else 1.0], [0.0])
+        return worst == 0.0
+
+    def make_manager(self, args):
+        from pmaf_b200 import planner
+
+        kw = dict(lanes_per_agent=args.lanes, block_threads=args.block, occupancy=args.occ)
+        if self.world == 1:
+            return planner.CfManager(self.local_rank, **kw)
         from pmaf_b200 import sharded
 
-        mgr = sharded.ShardedCfManager(local_rank, rank, world, lanes_per_agent=args.lanes, block_threads=args.block,
-                                       occupancy=args.occ)
-    feed = loop.ObstacleFeed(sc)
-    loop.plan_begin(mgr, sc)
+        return sharded.ShardedCfManager(self.local_rank, self.rank, self.world, **kw)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+
+def measure(env, args, sc1, steps, warmup, seeded_random=False):
+    """One workload: `warmup` untimed ticks, then `steps` device-timed ticks (value) and `steps` end-to-end
+    ticks (e2e). Returns the record (identical on every rank; rank 0 prints it)."""
+    world = env.world
+    # weak scaling: every GPU owns sc1.num_agents agents of a population of sc1.num_agents * world
+    sc = sc1 if world == 1 else sc1.with_(num_agents=sc1.num_agents * world,
+                                          name=sc1.name.replace(f"_{sc1.num_agents}x", f"_{sc1.num_agents * world}x"))
+    mgr = env.make_manager(args)
+    feed = loop.ObstacleFeed(sc)
+    if seeded_random:  # large sharded populations: the library draws each rank's vectors itself (shard-independent streams)
+        mgr.seed_random_vecs(sc.seed)
+    loop.plan_begin(mgr, sc, random_vecs=not seeded_random)
 
     def tick():
         out = mgr.tick(feed.pos, feed.vel, feed.rad, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
@@ -194,24 +238,23 @@ def run_ours(args, rank, world, local_rank):
         feed.step()
         return out
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         tick()
     mgr.stop_prediction()
     c0 = mgr.counters()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    env.barrier()
     dev_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         mgr.flush_l2()
         mgr.stop_prediction()
         mgr.timer_start()
         tick()
         dev_ms += mgr.timer_stop()  # waits for the rollout this tick launched
-    barrier()
+    env.barrier()
     c1 = mgr.counters()
     steps_local = c1["agent_steps_total"] - c0["agent_steps_total"]
     launches = c1["kernel_launches"] - c0["kernel_launches"]
-    rollout_ms = (c1["rollout_ms_total"] - c0["rollout_ms_total"]) / args.steps
+    rollout_ms = (c1["rollout_ms_total"] - c0["rollout_ms_total"]) / steps
 
     # ---- e2e: the reference-facing calls with host buffers, wall clock ----
     # the library's C++ host loop (pmaf_dry_run: planCallback's five CfManager calls per tick through the C ABI,
@@ -220,62 +263,128 @@ def run_ours(args, rank, world, local_rank):
     mgr.set_upload_dedup(False)
     mgr.stop_prediction()
     e0 = mgr.counters()
-    barrier()
+    env.barrier()
     n_feed = sc.num_obstacles - 1 if feed.active else 0
-    e2e_s, _, _, _ = mgr.dry_run(args.steps, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
+    e2e_s, _, _, _ = mgr.dry_run(steps, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
                                  sc.k_path_len, sc.k_safe_dist, sc.k_workspace, sc.ws_limits,
                                  feed_frequency=feed.frequency, wait_rollout=True, flush_l2=True)
     e1 = mgr.counters()
     e2e_steps_local = e1["agent_steps_total"] - e0["agent_steps_total"]
-    clocks = sampler.stop() if sampler else None  # sampled over both timed regions (device-resident and e2e)
+    (dev_ms, e2e_s, rollout_ms), (steps_all, e2e_steps_all) = env.reduce([dev_ms, e2e_s, rollout_ms],
+                                                                         [steps_local, e2e_steps_local])
+    O = sc.num_obstacles
+    steps_per_launch = steps_local / steps
+    alg_bytes = 24.0 * steps_per_launch + 128.0 * mgr.A + 56.0 * O
+    alg_flops = (40.0 * (O - 1) + 100.0) * steps_per_launch
+    rec = {
+        "value": steps_all / (dev_ms * 1e-3), "ms_per_step": dev_ms / steps, "steps": steps, "warmup": max(warmup, 3),
+        "config": workload_config(sc, world, {"lanes_per_agent": c1["lanes_per_agent"],
+                                              "block_threads": c1["block_threads"], "grid": c1["grid_blocks"],
+                                              "smem_bytes": c1["smem_bytes"], "occupancy_build": c1["occupancy_build"],
+                                              "best_agent_exchange": getattr(mgr, "exchange", "none (one GPU)")}),
+        "e2e": {"value": e2e_steps_all / e2e_s, "unit": "agent-steps/s",
+                "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) / steps,
+                "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) / steps,
+                "ms_per_step": 1e3 * e2e_s / steps,
+                "api": "pmaf_dry_run (C++ host loop): per tick stop_prediction, evaluate_agents, move_real_agent, "
+                       "get_next_position/velocity, reset_agents, start_prediction on host obstacle lists"},
+        "gpu_launches": int(launches),
+        "_kernel": {"ms": rollout_ms, "alg_bytes": alg_bytes, "alg_flops": alg_flops,
+                    "general_step_share": (c1["general_steps_total"] - c0["general_steps_total"]) / max(steps_local, 1)},
+    }
+    return rec, mgr
 
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    n = torch.tensor([steps_local, e2e_steps_local], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_s = t.tolist()
-    steps_all, e2e_steps_all = n.tolist()
 
+def roofline(rec, fp64_peak, peaks, peak_src, traffic):
+    """The roofline that binds is the FP64 pipe (~850 flop per byte at O = 256 against a machine balance
+    of ~5 flop/B for binary64), so `frac` is algorithmic binary64 flops / kernel time / the measured DFMA peak; the HBM
+    figure the contract asks for rides along under `hbm`."""
+    k = rec.pop("_kernel")
+    tf = k["alg_flops"] / (k["ms"] * 1e-3) / 1e12
+    gbs = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9
+    return {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+            "traffic": traffic, "peak_source": "measured in this run: independent DFMA chains on all SMs (pmaf_measure_fp64_peak)",
+            "algorithmic_flops": k["alg_flops"], "algorithmic_flops_per_agent_step": "40*(O-1)+100 (SURVEY.md §8d)",
+            "kernel": "rollout_kernel", "kernel_ms": k["ms"], "kernel_share_of_step": k["ms"] / rec["ms_per_step"],
+            "general_step_share": k["general_step_share"],
+            "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    "algorithmic_bytes": k["alg_bytes"], "peak_source": peak_src,
+                    "note": "24 B per agent-step + 128 B per agent + 56 B per obstacle: the path is not HBM-bound"}}
+
+
+def sharded_parity(env, args, name="near326_switching", ticks=3):
+    """N > 1: `ticks` control ticks of a golden case sharded over the ranks; best ids and the real agent's
+    states (replicated) and this rank's block of per-agent results must equal the reference's golden vectors
+    bit for bit. Returns "ok" or a description of the first mismatch (collective: every rank calls it)."""
+    from pmaf_b200 import cases, sharded
+
+    want = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    sc = cases.all_cases()[name].scenario
+    mgr = env.make_manager(args)
+    got = loop.run_closed_loop(mgr, sc, ticks)
+    first, end = sharded.shard_range(sc.num_agents, env.rank, env.world)
+    bad = []
+
+    def same(a, b):
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        if a.shape != b.shape:
+            return False
+        if b.dtype.kind == "f":
+            return bool(np.all((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))))
+        return bool(np.all(a == b))
+
+    for k in ("best", "next_pos", "next_vel", "goal_dist"):
+        if not same(got[k], want[k][:ticks]):
+            bad.append(k)
+    for k in ("steps", "length", "min_obs_dist", "reached"):
+        if not same(got[k], want[k][:ticks, first:end]):
+            bad.append(k)
+    if mgr.counters()["collectives"] < ticks:
+        bad.append("no exchange ran")
+    mgr.close()
+    ok = env.all_ok(not bad)
+    return "ok" if ok else f"MISMATCH (rank {env.rank}: {bad or 'another rank'})"
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libpmaf has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    env = Env(rank, world, local_rank)
+    parity = sharded_parity(env, args) if world > 1 else None
+    if parity not in (None, "ok"):
+        raise SystemExit(f"bench.py: sharded parity failed before timing: {parity}")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    rec, mgr = measure(env, args, WORKLOADS[args.workload](), args.steps, args.warmup)
+    fp64_peak = mgr.measure_fp64_peak()
+    mgr.close()
+    peaks, peak_src = measured_peaks()
+    line = {"metric": METRIC, "value": rec["value"], "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": rec["warmup"], "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": rec["config"], "e2e": rec["e2e"],
+            "gpu_launches": rec["gpu_launches"],
+            "roofline": roofline(rec, fp64_peak, peaks, peak_src, measured_traffic(args.workload) if world == 1 else None)}
+    if parity:
+        line["sharded_parity"] = parity
+    # ---- sub-records: the other BASELINE configs, time-boxed ----
+    subs = []
+    if not args.no_sub and args.workload == "c2":
+        names = ["c3", "c5", "c4s"] if world == 1 else ["c4s"]
+        for name in names:
+            r, m = measure(env, args, WORKLOADS[name](), SUB_TICKS, 3, seeded_random=(world > 1))
+            m.close()
+            r["roofline"] = roofline(r, fp64_peak, peaks, peak_src, measured_traffic(name) if world == 1 else None)
+            r.update({"name": name if world == 1 else "c4", "metric": METRIC, "unit": "agent-steps/s", "n_gpus": world})
+            subs.append(r)
+    line["workloads"] = subs
+    line["clocks"] = sampler.stop() if sampler else None
     if rank == 0:
-        peaks, peak_src = measured_peaks()
-        value = steps_all / (dev_ms * 1e-3)
-        O = sc.num_obstacles
-        steps_per_launch = steps_local / args.steps
-        alg_bytes = 24.0 * steps_per_launch + 128.0 * mgr.A + 56.0 * O
-        alg_flops = (40.0 * (O - 1) + 100.0) * steps_per_launch
-        hbm_achieved = alg_bytes / (rollout_ms * 1e-3) / 1e9
-        fp64_peak = mgr.measure_fp64_peak()
-        line = {
-            "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(sc, world, {"lanes_per_agent": c1["lanes_per_agent"],
-                                                  "block_threads": c1["block_threads"], "grid": c1["grid_blocks"],
-                                                  "smem_bytes": c1["smem_bytes"], "occupancy_build": c1["occupancy_build"],
-                                                  "best_agent_exchange": getattr(mgr, "exchange", "none (one GPU)")}),
-            "clocks": clocks,
-            "e2e": {"value": e2e_steps_all / e2e_s, "unit": "agent-steps/s",
-                    "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) / args.steps,
-                    "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) / args.steps,
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "pmaf_dry_run (C++ host loop): per tick stop_prediction, evaluate_agents, move_real_agent, "
-                           "get_next_position/velocity, reset_agents, start_prediction on host obstacle lists"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": measured_traffic(args.workload) if world == 1 else None,
-                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                         "kernel": "rollout_kernel", "kernel_ms": rollout_ms,
-                         "kernel_share_of_step": rollout_ms / (dev_ms / args.steps),
-                         "note": "the path is FP64-issue/latency bound, not HBM bound (SURVEY.md §8d); "
-                                 "see fp64_pipe for the roofline that binds",
-                         "fp64_pipe": {"achieved": alg_flops / (rollout_ms * 1e-3) / 1e12, "peak": fp64_peak,
-                                       "unit": "TFLOP/s",
-                                       "frac": alg_flops / (rollout_ms * 1e-3) / 1e12 / fp64_peak,
-                                       "peak_source": "measured here: dependent DFMA chains on all SMs"}},
-        }
         if world == 1 and not args.no_cpu:
-            est = sc.num_agents * sc.max_prediction_steps * O * 65e-9 / max(os.cpu_count() or 1, 1)
+            sc = WORKLOADS[args.workload]()
+            cores = host_threads()
+            est = sc.num_agents * sc.max_prediction_steps * sc.num_obstacles * 65e-9 / max(cores, 1)
             ticks = int(min(50, max(2, 15.0 / max(est, 1e-6))))
             v, seconds, kind, cores = time_cpu(sc, ticks)
             line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": kind,
@@ -283,9 +392,8 @@ def run_ours(args, rank, world, local_rank):
                                               f"{sc.num_agents} agents), pooled driver on {cores} host threads, "
                                               f"{seconds:.1f} s"}
         print(json.dumps(line), flush=True)
-    mgr.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if env.dist:
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -299,6 +407,7 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--occ", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records of the other BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -94,7 +94,14 @@ int pmaf_set_nccl_comm(pmaf_planner *p, void *nccl_comm);
  * distributes the handles (any transport), every rank imports all of them ([world][64], its own entry is
  * ignored). From then on evaluate_agents / tick run ONE kernel per rank that stores the rank's record
  * straight into every peer's block, waits for the peers' records and does the replicated selection.
- * Call both after pmaf_set_shard. If import fails (no peer access), the NCCL path stays in use. */
+ * Call both before or after pmaf_set_shard / pmaf_init (the block does not depend on the shard); the rank and
+ * world given to import must equal the shard's when evaluate runs. Every import needs a fresh export on ALL
+ * ranks (the export zeroes the block's sequence numbers and drops earlier mappings): a second import without
+ * one returns PMAF_ERR_STATE. If import fails (no peer access), the NCCL path stays in use.
+ * Failure: a peer whose record does not arrive within 2 s makes evaluate_agents / tick return PMAF_ERR_NCCL.
+ * That is FATAL for the whole sharded group — ranks that did complete the tick have moved on, so the replicas of
+ * the incumbent best agent may differ: every later evaluate on this handle fails the same way until all ranks
+ * have called pmaf_init again and re-done the export / import handshake. */
 int pmaf_p2p_export(pmaf_planner *p, unsigned char handle_out[64]);
 int pmaf_p2p_import(pmaf_planner *p, const unsigned char *handles /* [world][64] */, int rank, int world);
 

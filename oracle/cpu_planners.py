@@ -240,7 +240,9 @@ class _CpuPlanner:
         return known, rot
 
     def host_threads(self):
-        return self._fn("host_threads")()
+        """Threads the pooled driver runs on: the explicit count, else OpenMP's default (which a launcher
+        may have pinned to 1 through OMP_NUM_THREADS — pass `threads` to override it)."""
+        return self.threads if self.threads > 0 else self._fn("host_threads")()
 
 
 class RefPlanner(_CpuPlanner):

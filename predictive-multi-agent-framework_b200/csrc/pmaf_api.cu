@@ -110,6 +110,7 @@ struct pmaf_planner {
   DevBuf<unsigned char> xchg;          // this rank's exchange block
   unsigned char *peer_xchg[kP2pMaxWorld] = {};
   bool p2p_ready = false;
+  bool xchg_fresh = false;  // exported (zeroed) and not imported since: one import per export
   int p2p_rank = -1, p2p_world = 0;
   unsigned long long xseq = 0;
   DevBuf<unsigned long long> step_counter;
@@ -393,6 +394,7 @@ extern "C" int pmaf_p2p_export(pmaf_planner *p, unsigned char handle_out[64]) {
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, p->xchg.p));
   memcpy(handle_out, &h, 64);
+  p->xchg_fresh = true;
   return 0;
 }
 
@@ -400,7 +402,11 @@ extern "C" int pmaf_p2p_import(pmaf_planner *p, const unsigned char *handles, in
   ENTER(p);
   REQUIRE(handles && world >= 2 && world <= kP2pMaxWorld && rank >= 0 && rank < world, PMAF_ERR_ARG,
           "pmaf_p2p_import: bad argument (2 <= world <= %d)", kP2pMaxWorld);
-  REQUIRE(p->xchg.p != nullptr, PMAF_ERR_STATE, "pmaf_p2p_import: call pmaf_p2p_export first");
+  // one import per export: the export zeroes the block's sequence numbers (a second import would restart the
+  // sequence against stale flags) and drops earlier mappings (a second import would leak them)
+  REQUIRE(p->xchg.p != nullptr && p->xchg_fresh, PMAF_ERR_STATE,
+          "pmaf_p2p_import: call pmaf_p2p_export first (every import needs a fresh export on all ranks)");
+  p->xchg_fresh = false;
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
       p->peer_xchg[r] = p->xchg.p;
@@ -425,22 +431,8 @@ extern "C" int pmaf_p2p_import(pmaf_planner *p, const unsigned char *handles, in
 }
 
 // ---- lifecycle -------------------------------------------------------------------------------------------------
-extern "C" int pmaf_create(pmaf_planner **out, int device) {
-  REQUIRE(out != nullptr, PMAF_ERR_ARG, "pmaf_create: out is null");
-  *out = nullptr;
-  int n_dev = 0;
-  CU(cudaGetDeviceCount(&n_dev));
-  REQUIRE(device >= 0 && device < n_dev, PMAF_ERR_CUDA, "pmaf_create: CUDA device %d not available (%d visible)",
-          device, n_dev);
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  REQUIRE(prop.major == 10, PMAF_ERR_CUDA,
-          "pmaf_create: device %d is sm_%d%d; libpmaf is built for sm_100a only and has no fallback", device,
-          prop.major, prop.minor);
-  pmaf_planner *p = new (std::nothrow) pmaf_planner();
-  REQUIRE(p != nullptr, PMAF_ERR_ALLOC, "pmaf_create: out of host memory");
-  p->device = device;
-  CU(cudaSetDevice(device));
+static int create_resources(pmaf_planner *p) {
+  CU(cudaSetDevice(p->device));
   CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   for (int s = 0; s < 2; ++s)
     for (int e = 0; e < 2; ++e) CU(cudaEventCreate(&p->ev_roll[s][e]));
@@ -466,6 +458,33 @@ extern "C" int pmaf_create(pmaf_planner **out, int device) {
   CU(cudaMemsetAsync(p->real.p, 0, sizeof(RealState), p->stream));
   CU(cudaMemsetAsync(p->step_counter.p, 0, 16 * sizeof(unsigned long long), p->stream));
   CU(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+extern "C" int pmaf_destroy(pmaf_planner *p);
+
+extern "C" int pmaf_create(pmaf_planner **out, int device) {
+  REQUIRE(out != nullptr, PMAF_ERR_ARG, "pmaf_create: out is null");
+  *out = nullptr;
+  int n_dev = 0;
+  CU(cudaGetDeviceCount(&n_dev));
+  REQUIRE(device >= 0 && device < n_dev, PMAF_ERR_CUDA, "pmaf_create: CUDA device %d not available (%d visible)",
+          device, n_dev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  // the library holds sm_100a code only, and arch-specific ("a") code runs on exactly that architecture
+  REQUIRE(prop.major == 10 && prop.minor == 0, PMAF_ERR_CUDA,
+          "pmaf_create: device %d is sm_%d%d; libpmaf is built for sm_100a only and has no fallback", device,
+          prop.major, prop.minor);
+  pmaf_planner *p = new (std::nothrow) pmaf_planner();
+  REQUIRE(p != nullptr, PMAF_ERR_ALLOC, "pmaf_create: out of host memory");
+  p->device = device;
+  if (int rc = create_resources(p)) {
+    const std::string why = g_last_error;  // pmaf_destroy must not hide the cause
+    pmaf_destroy(p);
+    g_last_error = why;
+    return rc;
+  }
   *out = p;
   return 0;
 }
@@ -573,6 +592,7 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
           "pmaf_init: max_prediction_steps=%llu out of range", (unsigned long long)max_prediction_steps);
   if (int rc = finish_rollout(p)) return rc;
   CU(cudaStreamSynchronize(p->stream));
+  p->initialized = false;  // a failure below leaves the planner uninitialised, not half re-initialised
 
   // at least the HAD agent always exists (cf_manager.cpp:70-72); gains of a missing agent read as 0
   const int n_glob_in = std::max(n_agents, 1);

@@ -831,6 +831,7 @@ __global__ void __launch_bounds__(256) global_select_kernel(const unsigned char 
 // parity: a rank can be at most one tick ahead of another (its next selection needs everyone's next
 // record), so a slot is never overwritten before its reader is done.
 constexpr int kP2pMaxWorld = 16;
+constexpr unsigned long long kP2pWaitNs = 2000000000ull;  // 2 s: longest wait for a peer's record
 struct P2pExchange {
   unsigned char *peers[kP2pMaxWorld];  // every rank's exchange block as mapped into this process (own block included)
   int rank, world;
@@ -870,9 +871,12 @@ __global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *lo
   if (threadIdx.x < X.world) {
     volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(X.peers[X.rank] + p2p_flags_offset()) +
                                         parity * kP2pMaxWorld + threadIdx.x;
-    unsigned long long spins = 0;
+    // bounded by the global timer (a peer is gone: give up instead of hanging the GPU); the timer is read every
+    // 1024 polls only, it costs more than the poll itself
+    const unsigned long long t_start = global_timer_ns();
+    unsigned spins = 0;
     while (*flag != X.seq) {
-      if (++spins > (1ull << 27)) {  // ~ a second: a peer is gone; give up instead of hanging the GPU
+      if ((++spins & 1023u) == 0u && global_timer_ns() - t_start > kP2pWaitNs) {
         s_fail = 1;
         break;
       }
@@ -881,8 +885,11 @@ __global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *lo
   __threadfence_system();
   __syncthreads();
   if (s_fail) {
+    // A failed exchange is FATAL for the sharded planner group (pmaf.h, pmaf_p2p_import): the peers that did get
+    // every record go on, so the replicas of the incumbent may differ from here on. The host makes the flag sticky.
     if (threadIdx.x == 0) {
       *out_status = 1;
+      __threadfence_system();  // the status before the ticket
       if (host) host->seq[0] = ticket;  // wake the host; it reads out_status
     }
     return;

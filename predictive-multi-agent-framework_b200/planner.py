@@ -88,6 +88,7 @@ def load_library():
     lib.pmaf_nccl_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     lib.pmaf_p2p_export.argtypes = [H, C.c_char_p]
     lib.pmaf_p2p_import.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
+    lib.pmaf_get_section_cycles.argtypes = [H, C.POINTER(C.c_longlong)]
     lib.pmaf_init.argtypes = [H, _dp, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int,
                               _dp, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_double]
     lib.pmaf_seed_random_vecs.argtypes = [H, C.c_uint64]
@@ -192,7 +193,9 @@ class CfManager:
         op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
         ka, kc, kr, kd, km = (_f64(x, (-1,)) for x in (k_attr, k_circ, k_repel, k_damp, k_manip))
         kf = _f64(k_repel_force, (-1,))
-        if not (len(ka) == len(kc) == len(kr) == len(km)):  # the reference asserts this (cf_manager.cpp:50-51)
+        # the reference asserts k_attr/k_circ/k_repel/k_manip (cf_manager.cpp:50-51) and reads k_damp[i] for every
+        # agent as well (:73-104): a shorter k_damp is an out-of-bounds read there, an error here
+        if not (len(ka) == len(kc) == len(kr) == len(km)) or len(kd) < len(ka):
             raise PmafError(-1, "gain vectors differ in length")
         self._check(self.lib.pmaf_init(self.h, _d(_f64(goal, (3,))), float(delta_t), len(orad), _d(op), _d(ov),
                                        _d(orad), len(ka), _d(ka), _d(kc), _d(kr), _d(kd), _d(km), len(kf), _d(kf),

@@ -14,7 +14,9 @@ def assert_bit_identical(got, want, keys=None, ctx=""):
         a, b = np.asarray(got[k]), np.asarray(want[k])
         assert a.shape == b.shape, f"{ctx}{k}: shape {a.shape} != {b.shape}"
         if b.dtype.kind == "f":
-            same = (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+            # bit patterns, so +0.0 and -0.0 differ; any NaN matches any NaN (payloads are not part of the contract)
+            a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+            same = (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))
         else:
             same = a == b
         if not np.all(same):

@@ -145,9 +145,9 @@ def test_baseline_config_against_oracle(make, ticks):
     want = loop.run_closed_loop(_oracle(), sc, ticks, record_paths=True)
     got = loop.run_closed_loop(_planner(), sc, ticks, record_paths=True)
     REPORT[sc.name] = _bit_stats(dict(got, final_paths=got["paths"]), dict(want, final_paths=want["paths"]))
-    assert_bit_identical(got, want, keys=("best", "steps", "reached"), ctx=f"{sc.name}: ")
     assert_close(got, want, RTOL, keys=("next_pos", "next_vel", "length", "min_obs_dist", "goal_dist", "paths"),
-                 ctx=f"{sc.name}: ")
+                 ctx=f"{sc.name}: ")  # north_star's tolerance ...
+    assert_bit_identical(got, want, ctx=f"{sc.name}: ")  # ... and the bar this build holds itself to
     # every integration step executes on these workloads
     assert int(got["steps"][-1].sum()) == sc.num_agents * sc.max_prediction_steps
 

@@ -21,7 +21,10 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        # lane utilisation: threads per executed warp instruction, all / with their predicate on
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__thread_inst_executed_pred_on_per_inst_executed.ratio",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active"]
 
 
 def ncu(rep, *args):
@@ -46,7 +49,8 @@ def main():
         except ValueError:
             pass
     tot = sum(ops.values())
-    tma = {k: ops[k] for k in ("UBLKCP", "SYNCS", "REDUX", "MUFU", "SHFL") if k in ops}
+    # warp-wide integer minima compile to CREDUX (redux.sync), the bulk copy to UBLKCP, its mbarrier to SYNCS
+    tma = {k: ops.get(k, 0) for k in ("UBLKCP", "SYNCS", "CREDUX", "REDUX", "MUFU", "SHFL", "BAR", "WARPSYNC")}
     def f(name):
         return float(metrics[name]["value"].replace(",", ""))
     out = {"kernel": desc, "metrics": metrics,
