@@ -818,13 +818,13 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
   // 170-register build beyond (C3: 4096, C4 shard: 8192 agents) — unless the scene is static with more than
   // 64 field obstacles, where the latency build's chunked straight-line step (MULTI) is used
   const bool multi_ok = LPA == 32 && !dynamic && p->O - 1 > kBroadUnrolledRounds * 32 && block <= 256;
-  if (occ == 0) occ = (block <= 128 && (long long)grid * block / 32 > 12 * 148 && !multi_ok) ? 3 : 1;
-  if (LPA < 16 || block > 128) occ = 1;  // the occupancy builds exist for 16/32 lanes per agent, CTAs <= 128 threads
+  if (occ == 0) occ = (LPA == 32 && block <= 128 && (long long)grid * block / 32 > 12 * 148 && !multi_ok) ? 3 : 1;
+  if (LPA < 8 || block > 128) occ = 1;  // the occupancy builds exist for 8/16/32 lanes per agent, CTAs <= 128 threads
   auto kern = dynamic ? rollout_kernel<LPA, true, 1> : rollout_kernel<LPA, false, 1>;
   if constexpr (LPA == 32) {
     if (occ == 1 && multi_ok) kern = rollout_kernel<32, false, 1, true>;
   }
-  if constexpr (LPA >= 16) {
+  if constexpr (LPA >= 8) {
     if (occ == 3) kern = dynamic ? rollout_kernel<LPA, true, 3> : rollout_kernel<LPA, false, 3>;
 
     if (occ == 4) kern = dynamic ? rollout_kernel<LPA, true, 4> : rollout_kernel<LPA, false, 4>;
@@ -836,15 +836,21 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
 }
 
 static void pick_rollout_shape(const pmaf_planner *p, int &lpa, int &block) {
-  lpa = p->tune_lpa ? p->tune_lpa : 32;
+  // One warp per agent (32 lanes) while the population fits the machine about twice over (8 resident warps per SM
+  // at 255 registers: 1184 agents in flight); beyond that 4 agents share a warp (8 lanes each, fast_step_packed):
+  // measured on B200, 4096 agents x 256 obstacles 6.8 -> 5.0 ms, 8192 x 1024 15.3 -> 10.9 ms, while 1024 agents
+  // x 50 moving obstacles lose (0.65 -> 0.78 ms: a packed warp's step is a longer dependency chain).
+  lpa = p->tune_lpa ? p->tune_lpa : (p->A >= 3072 ? 8 : 32);
   if (p->tune_block) {
     block = p->tune_block;
   } else {
-    // small populations are latency-bound: one warp per CTA spreads them over all 148 SMs;
-    // large ones pack 2 warps per CTA (measured best on 4096 agents x 256 obstacles) and use the
-    // 170-register build so that 6+ warps stay resident per SM
+    // small populations are latency-bound: one warp per CTA spreads them over all 148 SMs; large ones pack
+    // 2 warps per CTA (measured best on 4096 agents x 256 obstacles with one warp per agent), packed shapes a
+    // whole SM's worth (8 warps share one obstacle image)
     const long long warps = ((long long)p->A * lpa + 31) / 32;
-    block = warps <= 2 * 148 ? 32 : 64;
+    block = warps <= 2 * 148 ? 32 : (lpa < 32 && warps >= 8 * 128 ? 256 : 64);
+    // the obstacle image plus the per-agent lists must fit 227 KB
+    while (block > 32 && block > lpa && rollout_smem_bytes(p->img, block / lpa, lpa, p->known_words) > 227 * 1024) block /= 2;
   }
   if (block < lpa) block = lpa;
 }

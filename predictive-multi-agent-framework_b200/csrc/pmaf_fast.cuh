@@ -352,16 +352,20 @@ __device__ __forceinline__ bool fast_step(const Group<32> &g, const StepEnv &P, 
 #undef PMAF_RARE
 }
 
-// The same step for obstacle sets whose candidates do not fit one lane each (more than 64 field
-// obstacles: the broad phase is a loop, the narrow phase runs in chunks of 32 candidates). Per chunk the
-// straight-line narrow phase of fast_step; contributions are summed chunk after chunk (candidate order =
-// obstacle order), the per-lane running minima are reduced once after the last chunk, and
-// attractorForceScaling's tail is evaluated once for the winner (these populations run several warps per
-// scheduler: fewer instructions beat a shorter dependency chain). First detections are committed chunk by
-// chunk: a later rare event re-runs the general step, which then finds the obstacle known with exactly the
-// rotation vector it would have latched itself.
-template <bool STATIC_VEL>
-__device__ __forceinline__ bool fast_step_multi(const Group<32> &g, const StepEnv &P, const SmemObstacles &obs,
+// The same step for the THROUGHPUT shapes: obstacle sets whose candidates do not fit one lane each (more than
+// 64 field obstacles: the broad phase is a loop) and groups narrower than a warp (G = Group<16> / Group<8>:
+// two / four agents share a warp's instruction stream, so the scalar part of the step, the ordered force sum
+// and the reductions are issued once for 2 / 4 agents instead of once per agent, and a candidate list of n
+// entries occupies ceil(n / LPA) * LPA lane slots instead of ceil(n / 32) * 32). The narrow phase runs in
+// chunks of G::kLanes candidates. Per chunk the straight-line narrow phase of fast_step; contributions are
+// summed chunk after chunk (candidate order = obstacle order), the per-lane running minima are reduced once
+// after the last chunk, and attractorForceScaling's tail is evaluated once for the winner (these populations
+// run several warps per scheduler: fewer instructions beat a shorter dependency chain). First detections are
+// committed chunk by chunk: a later rare event re-runs the general step, which then finds the obstacle known
+// with exactly the rotation vector it would have latched itself. All collectives are the group's (sub-warp
+// masks), all branches are group-uniform; groups of one warp may diverge from each other.
+template <bool STATIC_VEL, class G>
+__device__ __forceinline__ bool fast_step_multi(const G &g, const StepEnv &P, const SmemObstacles &obs,
                                                 const uint16_t *cand, double *fbuf, const KnownBits &known, int type,
                                                 const AgentConsts &c, const FastConsts &fc, v3 init_pos, double *rot_row,
                                                 const double *random_row, v3 goal_vec, const Prologue &pr, v3 &p,
@@ -381,14 +385,16 @@ __device__ __forceinline__ bool fast_step_multi(const Group<32> &g, const StepEn
   v3 force = mk3(0.0, 0.0, 0.0);
   double lmin = (double)INFINITY, lcd = (double)INFINITY;  // per-lane running minima over the chunks
   int lci = 0x7fffffff;                                    // candidate position of the lane's closest obstacle
-  const unsigned lt_mask = (1u << g.lane) - 1u;
+  constexpr int LPA = G::kLanes;
+  static_assert(LPA >= kFastSumUnroll, "the zero padding of the staging buffer is written by the group's first lanes");
+  const unsigned lt_mask = g.mask & ((1u << g.lane) - 1u);
   const bool uses_rot = (fc.tbits & kTUsesRot) != 0;
-  constexpr int kFbufSlots = 32 + kFastSumUnroll;
+  constexpr int kFbufSlots = LPA + kFastSumUnroll;
   double *fx = fbuf, *fy = fbuf + kFbufSlots, *fz = fbuf + 2 * kFbufSlots;
   const double2 *fx2 = reinterpret_cast<const double2 *>(fx), *fy2 = reinterpret_cast<const double2 *>(fy),
                 *fz2 = reinterpret_cast<const double2 *>(fz);
   g.sync();  // cand[] was written by the broad phase
-  for (int c0 = 0; c0 < n_cand; c0 += 32) {
+  for (int c0 = 0; c0 < n_cand; c0 += LPA) {
     const int ci = c0 + g.gl;
     const bool active = ci < n_cand;
     const int i = (int)cand[active ? ci : 0];
@@ -428,7 +434,7 @@ __device__ __forceinline__ bool fast_step_multi(const Group<32> &g, const StepEn
             const v3 o_id = obs.pos(id);
             double best = 100.0;
             int best_i = 0x7fffffff;
-            for (int k = g.gl; k < n_field; k += 32) {
+            for (int k = g.gl; k < n_field; k += LPA) {
               const v3 dk = sub3(o_id, obs.pos(k));
               const double dist = fscan.sqrt_(k != id ? dot3(dk, dk) : 1.0);
               if ((k != id) & (best > dist)) best = dist, best_i = k;
@@ -518,7 +524,7 @@ __device__ __forceinline__ bool fast_step_multi(const Group<32> &g, const StepEn
       const double2 x = fx2[j], y = fy2[j], z2 = fz2[j];
       force = add3(add3(force, mk3(x.x, y.x, z2.x)), mk3(x.y, y.y, z2.y));
     }
-    if (n_contrib > kFastSumUnroll) {
+    if (LPA > kFastSumUnroll && n_contrib > kFastSumUnroll) {  // narrow groups: a chunk never holds more
       for (int j = kFastSumUnroll / 2; 2 * j < n_contrib; j += 2) {
         const double2 x0 = fx2[j], y0 = fy2[j], z0 = fz2[j], x1 = fx2[j + 1], y1 = fy2[j + 1], z1 = fz2[j + 1];
         force = add3(add3(force, mk3(x0.x, y0.x, z0.x)), mk3(x0.y, y0.y, z0.y));
@@ -566,6 +572,256 @@ __device__ __forceinline__ bool fast_step_multi(const Group<32> &g, const StepEn
   if (vel_norm > c.vel_max) nvel = mul3(nvel, scale);
   rare |= fm.bad();
   if (__builtin_expect(rare, 0)) return false;
+  p = np, v = nvel, min_obs = new_min_obs;
+  return true;
+}
+
+// ---- packed shapes: 2 / 4 agents per warp -------------------------------------------------------------------------
+// fast_step_multi's arithmetic with the control flow of a warp that carries several agents: every lane of the
+// WARP executes the same instruction stream (chunk loop up to the largest candidate count among the warp's
+// groups, warp-uniform branches around the cold blocks) and all collectives are the warp-convergent `_w`
+// variants — a group whose agent has no work in a chunk (fewer candidates, closed gate, finished or absent
+// agent) runs predicated off on a valid dummy candidate and commits nothing. What the warp issues once now
+// serves 2 / 4 agents: the scalar part of the step, the ordered force sum (its dependent adds are the longest
+// serial chain of a step), the reductions and the loop overhead; a candidate list of n entries occupies
+// ceil(n / LPA) * LPA lane slots instead of ceil(n / 32) * 32. A closed gate (cf_agent.cpp:315-317) is part of
+// this path (zero candidates), so that only termination and the rare events leave it.
+// Returns true when the group's step was taken (p, v, min_obs updated); false: nothing of the step's state
+// changed (first detections may have been latched, exactly as the general step will find them), the caller
+// decides between termination and the general step.
+template <bool STATIC_VEL, class G>
+__device__ __forceinline__ bool fast_step_packed(const G &g, const StepEnv &P, const SmemObstacles &obs,
+                                                 const uint16_t *cand, double *fbuf, const KnownBits &known, int type,
+                                                 const AgentConsts &c, const FastConsts &fc, v3 init_pos, double *rot_row,
+                                                 const double *random_row, v3 goal_vec, const Prologue &pr, v3 &p,
+                                                 v3 &v, double &min_obs, bool step_on, const uint16_t *nn_table) {
+  constexpr int LPA = G::kLanes;
+  static_assert(LPA >= kFastSumUnroll, "the zero padding of the staging buffer is written by the group's first lanes");
+  const StepNorms &sn = pr.sn;
+  const v3 d0 = sub3(p, init_pos);
+  const double z0 = dot3(d0, d0);
+  const bool near_start = z0 < fc.thr_start.lo;
+  const bool start_ambiguous = !near_start & !(z0 > fc.thr_start.hi);
+  const bool gate_open = !(sn.dist_goal < c.approach_dist) & !((sn.vn < c.half_vmax) & near_start);
+  const bool eligible = step_on & fc.usable & !start_ambiguous;
+  const int n_cand = (eligible & gate_open) ? pr.n_cand : 0;  // closed gate: no field pass at all (:315-318)
+  const int n_max = __reduce_max_sync(0xffffffffu, n_cand);
+  const v3 dvs = sub3(p, obs.pos(P.n_obs - 1));
+  bool rare = !(dot3(dvs, dvs) > c.repel_far2);  // repelForce (:159-181): the sentinel must be out of its shell
+
+  v3 force = mk3(0.0, 0.0, 0.0);
+  double lmin = (double)INFINITY, lcd = (double)INFINITY;  // per-lane running minima over the chunks
+  int lci = 0x7fffffff;                                    // candidate position of the lane's closest obstacle
+  const unsigned lt_mask = (1u << g.gl) - 1u;
+  const bool uses_rot = (fc.tbits & kTUsesRot) != 0;
+  constexpr int kFbufSlots = LPA + kFastSumUnroll;
+  double *fx = fbuf, *fy = fbuf + kFbufSlots, *fz = fbuf + 2 * kFbufSlots;
+  const double2 *fx2 = reinterpret_cast<const double2 *>(fx), *fy2 = reinterpret_cast<const double2 *>(fy),
+                *fz2 = reinterpret_cast<const double2 *>(fz);
+  g.sync_w();  // cand[] was written by the broad phase
+  for (int c0 = 0; c0 < n_max; c0 += LPA) {
+    const int ci = c0 + g.gl;
+    const bool active = ci < n_cand;
+    const int ci_safe = active ? ci : 0;
+    const int i_raw = (int)cand[ci_safe];
+    const int i = active ? i_raw : 0;  // an idle lane shadows obstacle 0 (cand[0] may never have been written)
+    const v3 oi = obs.pos(i);
+    const double rs = obs.rsum(i);
+    const bool is_known = active & known.test(i);
+    v3 rot_i = mk3(0.0, 0.0, 1.0);
+    if (uses_rot & is_known) rot_i = ld3(rot_row + 3 * i);
+    const v3 rov = sub3(oi, p);
+    const v3 rel = STATIC_VEL ? v : sub3(v, obs.vel(i));
+    FastMath fa, fb;
+    const double z = dot3(rov, rov);
+    double n, yn;
+    fa.sqrt_rcp_(z, n, yn);
+    const v3 to_obs = fa.quot3_(rov, n, yn);
+    const double d = clamp_dist(n - rs);
+    const bool skip = (dot3(to_obs, pr.ghat) < -0.01) & (dot3(rov, rel) < -0.01);  // :79-82
+    const bool counts = active & !skip;
+    const bool close = active & (d < c.shell);
+    const bool in_shell = close & !skip;
+    const bool first_seen = in_shell & !is_known;
+    bool latch_flag = false;
+    if (first_seen & ((fc.tbits & kTRandom) != 0)) rot_i = cross3(pr.ghat, ld3(random_row + 3 * i));
+    // HAD and the two obstacle heuristics (agents 0, 2, 3 of the population): cold, warp-uniform test
+    const bool cold_mine = first_seen & ((fc.tbits & (kTUsesRot | kTRandom)) == kTUsesRot);
+    if (__builtin_expect(g.any_w(cold_mine), 0)) {
+      FastMath fscan, frot;
+      int nn = 0;
+      const bool need_nn = cold_mine & ((fc.tbits & kTNeedsNN) != 0);
+      if (nn_table) {  // static scene: per-tick table built by reset_kernel
+        if (need_nn) nn = nn_table[i];
+      } else {  // nearest other field obstacle, serial-scan semantics (:434-446); the whole warp scans for one lane
+        unsigned todo = __ballot_sync(0xffffffffu, need_nn);
+        const int n_field = P.n_obs - 1;
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int id = __shfl_sync(0xffffffffu, i, src);
+          const v3 o_id = obs.pos(id);
+          double best = 100.0;
+          int best_i = 0x7fffffff;
+          for (int k = g.lane; k < n_field; k += 32) {
+            const v3 dk = sub3(o_id, obs.pos(k));
+            const double dist = fscan.sqrt_(k != id ? dot3(dk, dk) : 1.0);
+            if ((k != id) & (best > dist)) best = dist, best_i = k;
+          }
+          {  // lexicographic (distance, index) minimum over the warp: redux on the integer order of non-negative doubles
+            const unsigned hi = (unsigned)__double2hiint(best), lo = (unsigned)__double2loint(best);
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+            const bool mine = (hi == mhi) & (lo == mlo);
+            best_i = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)best_i : 0xffffffffu);
+          }
+          if (g.lane == src) nn = best_i == 0x7fffffff ? 0 : best_i;
+        }
+      }
+      if (cold_mine) {  // lane-divergent, no collectives inside
+        v3 r;
+        if (type == HAD_HEURISTIC) {  // rot_had (:599-611)
+          const double sh = frot.div_(dot3(rov, goal_vec), sn.dist_goal * sn.dist_goal);
+          const v3 dh = sub3(add3(p, mul3(goal_vec, sh)), oi);
+          const v3 ch = cross3(dh, goal_vec);
+          double nh, yh;
+          frot.sqrt_rcp_(dot3(ch, ch), nh, yh);
+          r = frot.quot3_(ch, nh, yh);
+        } else {  // rot_obstacle (:447-460), rot_goal_obstacle (:493-517)
+          const v3 obstacle_vec = sub3(obs.pos(nn), oi);
+          const v3 obst_current = sub3(mul3(to_obs, dot3(obstacle_vec, to_obs)), obstacle_vec);
+          v3 cur = obst_current;
+          if (type == GOAL_OBSTACLE_HEURISTIC) {
+            const v3 goal_current = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+            double n1, y1, n2, y2, n3, y3;
+            frot.sqrt_rcp_(dot3(goal_current, goal_current), n1, y1);
+            frot.sqrt_rcp_(dot3(obst_current, obst_current), n2, y2);
+            cur = add3(frot.quot3_(goal_current, n1, y1), frot.quot3_(obst_current, n2, y2));
+            FastMath fsum;  // a sum below 1e-10 is replaced, whatever its square root did
+            fsum.sqrt_rcp_(dot3(cur, cur), n3, y3);
+            const v3 q3 = fsum.quot3_(cur, n3, y3);
+            const bool tiny = n3 < 1e-10;
+            frot.flag |= (fsum.bad() && !(dot3(cur, cur) == 0.0)) ? 1u : 0u;
+            cur = (tiny | (dot3(cur, cur) == 0.0)) ? mk3(0.0, 0.0, 1.0) : q3;
+          }
+          const v3 cr = cross3(cur, to_obs);
+          double nr, yr;
+          frot.sqrt_rcp_(dot3(cr, cr), nr, yr);
+          r = frot.quot3_(cr, nr, yr);
+        }
+        rot_i = r;
+        latch_flag = frot.bad();
+      }
+      latch_flag |= g.any_w(fscan.bad());  // an operand of the shared scan out of range: every group re-runs
+    }
+    double zr, vel_norm;
+    v3 nv;
+    if (STATIC_VEL) {
+      zr = sn.zv, vel_norm = sn.vn, nv = pr.nv_static;
+    } else {
+      double yv;
+      zr = dot3(rel, rel);
+      fb.sqrt_rcp_(zr, vel_norm, yv);
+      nv = fb.quot3_(rel, vel_norm, yv);
+    }
+    const v3 nv_eigen = zr > 0.0 ? nv : rel;
+    v3 cin = cross3(to_obs, rot_i);
+    if (fc.tbits & kTGoal) cin = sub3(goal_vec, mul3(to_obs, dot3(to_obs, goal_vec)));
+    if (fc.tbits & kTVel) cin = sub3(nv_eigen, mul3(to_obs, dot3(nv_eigen, to_obs)));
+    double nc, yc;
+    fb.sqrt_rcp_(dot3(cin, cin), nc, yc);
+    v3 current = fb.quot3_(cin, nc, yc);
+    if (!uses_rot & (nc < 1e-10)) current = mk3(0.0, 0.0, 1.0);
+    const v3 f = mul3(cross3(nv, cross3(current, nv)), fb.div_(c.k_circ, d * d));
+    const bool contributes = in_shell & (vel_norm != 0);
+    const bool lane_bad = latch_flag | (active & (fa.bad() | (close & fb.bad())));
+    // running minima (strict <: the first of equals within a lane has the lower obstacle index)
+    if (counts & (d < lmin)) lmin = d;
+    if (close & (d < lcd)) lcd = d, lci = ci;
+    // ordered sum of this chunk's contributions (group-relative ballots)
+    const unsigned contrib = g.ballot_w(contributes);
+    const int n_contrib = __popc(contrib);
+    if (contributes) {
+      const int rk = __popc(contrib & lt_mask);
+      fx[rk] = f.x, fy[rk] = f.y, fz[rk] = f.z;
+    }
+    if (g.gl < kFastSumUnroll) fx[n_contrib + g.gl] = 0.0, fy[n_contrib + g.gl] = 0.0, fz[n_contrib + g.gl] = 0.0;
+    const bool any_bad = g.ballot_w(lane_bad) != 0u;
+    rare |= any_bad;
+    // first detections of this chunk (:93-95); not while an operand of the group was out of range
+    if (__builtin_expect(g.any_w(first_seen), 0)) {
+      if (first_seen & !any_bad) {
+        st3(rot_row + 3 * i, rot_i);
+        known.set(i);
+      }
+    }
+    g.sync_w();
+#pragma unroll
+    for (int j = 0; j < kFastSumUnroll / 2; ++j) {
+      const double2 x = fx2[j], y = fy2[j], z2 = fz2[j];
+      force = add3(add3(force, mk3(x.x, y.x, z2.x)), mk3(x.y, y.y, z2.y));
+    }
+    if (LPA > kFastSumUnroll) {  // narrower groups: a chunk never holds more than the unrolled block
+      if (g.any_w(n_contrib > kFastSumUnroll)) {  // zero-padded past n_contrib: groups with fewer add +0.0 (exact)
+        const int n_more = __reduce_max_sync(0xffffffffu, n_contrib);
+        for (int j = kFastSumUnroll / 2; 2 * j < n_more; j += 2) {
+          const bool on = 2 * j < n_contrib;  // beyond the group's own padding the buffer holds stale values
+          const double2 x0 = fx2[j], y0 = fy2[j], z0 = fz2[j], x1 = fx2[j + 1], y1 = fy2[j + 1], z1 = fz2[j + 1];
+          v3 fn = add3(add3(force, mk3(x0.x, y0.x, z0.x)), mk3(x0.y, y0.y, z0.y));
+          fn = add3(add3(fn, mk3(x1.x, y1.x, z1.x)), mk3(x1.y, y1.y, z1.y));
+          if (on) force = fn;
+        }
+      }
+    }
+    g.sync_w();
+  }
+  // reductions over the lanes' running minima
+  const double min_d = g.min_w_nonneg(lmin);
+  const bool has_closest = g.ballot_w(lci != 0x7fffffff) != 0u;
+  double kgs_closest = 1.0;
+  bool kgs_bad = false;
+  if (g.any_w(has_closest)) {  // attractorForceScaling's tail (:212-226) once, for the first obstacle with the smallest distance
+    g.argmin_w_nonneg(lcd, lci);
+    const int ic_raw = (int)cand[has_closest ? lci : 0];
+    const v3 o_c = obs.pos(has_closest ? ic_raw : 0);
+    FastMath fs;
+    kgs_closest = attractor_scaling(fs, goal_vec, sn.dist_goal, p, v, sn.vn, c, has_closest ? lcd : 1.0, o_c);
+    kgs_bad = has_closest & fs.bad();
+  }
+  rare |= kgs_bad;
+  // ---- scalar rest of the step (as in fast_step) ----
+  const double new_min_obs = min_d < min_obs ? min_d : min_obs;
+  const double fzz = dot3(force, force);
+  const bool big = fzz > fc.thr_force.hi;
+  rare |= !big & !(fzz < fc.thr_force.lo);
+  const double k_goal_scale = (has_closest & big) ? kgs_closest : 1.0;
+  force = add3(force, mk3(0.0, 0.0, 0.0));
+  const v3 fa3 = add3(force, mul3(sub3(sn.vel_des, v), k_goal_scale * c.k_damp));
+  if (c.k_attr != 0.0) force = fa3;
+  {
+    const double zacc = dot3(force, force);
+    const bool clamp = zacc > fc.thr_acc.hi;
+    rare |= !clamp & !(zacc < fc.thr_acc.lo);
+    if (__builtin_expect(g.any_w(clamp), 0)) {
+      FastMath fc2;
+      double na, ya;
+      fc2.sqrt_rcp_(zacc, na, ya);
+      const v3 fcl = mul3(force, fc2.quot_(13.0, na, ya));
+      if (clamp) force = fcl;
+      rare |= clamp & fc2.bad();
+    }
+  }
+  const double dt = P.pred_dt;
+  const v3 np = mk3((p.x + 0.5 * force.x * dt * dt) + v.x * dt, (p.y + 0.5 * force.y * dt * dt) + v.y * dt,
+                    (p.z + 0.5 * force.z * dt * dt) + v.z * dt);
+  v3 nvel = add3(v, mul3(force, dt));
+  FastMath fm;
+  double vel_norm, yvn;
+  fm.sqrt_rcp_(dot3(nvel, nvel), vel_norm, yvn);
+  const double scale = fm.quot_(c.vel_max, vel_norm, yvn);
+  if (vel_norm > c.vel_max) nvel = mul3(nvel, scale);
+  rare |= fm.bad();
+  if (rare | !eligible) return false;
   p = np, v = nvel, min_obs = new_min_obs;
   return true;
 }

@@ -236,6 +236,44 @@ struct Group {
     const unsigned mi = __reduce_min_sync(mask, v == m ? (unsigned)idx : 0xffffffffu);
     v = m, idx = (int)mi;
   }
+  // ---- warp-convergent variants ("_w") ----------------------------------------------------------------------
+  // A collective with a sub-warp member mask that differs between the lanes of a warp (2 / 4 agents per warp)
+  // compiles to MATCH.ANY + a divergent loop over the distinct masks: every group is served on its own and
+  // the warp's instruction stream is issued once per group. The _w variants are executed by ALL 32 lanes of
+  // the warp together (every group at once, constant full mask) and hand each group its own part of the
+  // result; ballots are returned GROUP-RELATIVE (bit j = lane j of this group). The straight-line step of the
+  // packed shapes (fast_step_packed) uses nothing else; for LPA == 32 they are the plain collectives.
+  __device__ __forceinline__ unsigned ballot_w(bool p) const {
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    return LPA == 32 ? m : (m >> lane0) & ((1u << (LPA & 31)) - 1u);
+  }
+  __device__ __forceinline__ bool any_w(bool p) const { return __any_sync(0xffffffffu, p) != 0; }  // the whole WARP
+  __device__ __forceinline__ void sync_w() const { __syncwarp(); }
+  __device__ __forceinline__ double bcast_w(double v, int group_lane) const { return __shfl_sync(0xffffffffu, v, lane0 + group_lane); }
+  __device__ __forceinline__ int bcast_w(int v, int group_lane) const { return __shfl_sync(0xffffffffu, v, lane0 + group_lane); }
+  // minimum of non-negative doubles (or +inf) over the group: redux for a whole warp, xor butterflies
+  // (which stay inside aligned groups) otherwise
+  __device__ __forceinline__ double min_w_nonneg(double v) const {
+    if (LPA == 32) return min_reduce_nonneg(v);
+#pragma unroll
+    for (int off = LPA / 2; off > 0; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, v, off);
+      v = o < v ? o : v;
+    }
+    return v;
+  }
+  __device__ __forceinline__ void argmin_w_nonneg(double &v, int &idx) const {
+    if (LPA == 32) {
+      argmin_reduce_nonneg(v, idx);
+      return;
+    }
+#pragma unroll
+    for (int off = LPA / 2; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+      if (ov < v || (ov == v && oi < idx)) v = ov, idx = oi;
+    }
+  }
   // lexicographic (value, index) minimum: smallest value, lowest index among equals
   __device__ __forceinline__ void argmin_reduce(double &v, int &idx) const {
 #pragma unroll

@@ -11,13 +11,19 @@ constexpr int kFastSumUnroll = 8;
 // Shared memory of a rollout CTA:
 //   [0, 16)                      mbarrier
 //   [16, 16 + img.bytes)         obstacle image (TMA bulk copy of PlannerDev::image)
-//   then per group: double fbuf[3 * (LPA + 8)] (ordered force sum staging), uint16 cand[cand_stride],
-//   uint32 known[known_words]
-__host__ __device__ inline uint32_t rollout_cand_stride(int n_obs) { return (uint32_t)((n_obs + 7) & ~7); }
+//   then per group: double fbuf[fbuf_stride] (ordered force sum staging, 3 * (LPA + 8) used), uint16
+//   cand[cand_stride], uint32 known[known_words]
+// Per-group strides are padded so that the groups of one warp (2 / 4 agents per warp) fall into different banks
+// when they read their own list / staging buffer at the same offset: stride = 4 words (16 B) mod 32 words.
+__host__ __device__ inline uint32_t rollout_cand_stride(int n_obs) { return (uint32_t)(((n_obs + 63) & ~63) + 8); }
+__host__ __device__ inline uint32_t rollout_fbuf_stride(int lanes_per_agent) {
+  const uint32_t n = 3u * (uint32_t)(lanes_per_agent + kFastSumUnroll);  // doubles
+  return n + ((34u - (n & 15u)) & 15u);  // (2 * stride) mod 32 words == 4: stride mod 16 doubles == 2
+}
 __host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, int groups, int lanes_per_agent,
                                                      int known_words) {
   size_t b = 16 + img.bytes;
-  b += (size_t)groups * 3 * (lanes_per_agent + kFastSumUnroll) * sizeof(double);
+  b += (size_t)groups * rollout_fbuf_stride(lanes_per_agent) * sizeof(double);
   b += (size_t)groups * rollout_cand_stride(img.n_obs) * sizeof(uint16_t);
   b += (size_t)groups * known_words * sizeof(uint32_t);
   return (b + 15) & ~(size_t)15;
@@ -92,6 +98,40 @@ PMAF_HDT int broad_phase_loop(const G &g, const float4 *bp, int n_field, v3 p, u
     for (int r = 0; r < R; ++r) {
       if (c[r]) cand[n_cand + PMAF_POPC(m[r] & lt_mask)] = (uint16_t)(base + r * LPA + g.gl);
       n_cand += PMAF_POPC(m[r]);
+    }
+  }
+  return n_cand;
+}
+
+// The same loop with warp-convergent collectives (Group::ballot_w): every lane of the warp runs it, each group
+// compacts its own list (2 / 4 agents per warp).
+template <class G>
+__device__ __forceinline__ int broad_phase_loop_w(const G &g, const float4 *bp, int n_field, v3 p, uint16_t *cand) {
+  constexpr int LPA = G::kLanes;
+  const float fx = (float)p.x, fy = (float)p.y, fz = (float)p.z;
+  const unsigned lt_mask = (1u << g.gl) - 1u;
+  int n_cand = 0;
+  constexpr int R = 4;
+  for (int base = 0; base < n_field; base += R * LPA) {
+    float4 b[R];
+    bool c[R];
+    unsigned m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = base + r * LPA + g.gl;
+      b[r] = bp[i < n_field ? i : n_field];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = base + r * LPA + g.gl;
+      const float dx = b[r].x - fx, dy = b[r].y - fy, dz = b[r].z - fz;
+      c[r] = (i < n_field) & (dx * dx + dy * dy + dz * dz < b[r].w);
+      m[r] = g.ballot_w(c[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (c[r]) cand[n_cand + __popc(m[r] & lt_mask)] = (uint16_t)(base + r * LPA + g.gl);
+      n_cand += __popc(m[r]);
     }
   }
   return n_cand;
@@ -249,7 +289,8 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   unsigned char *img = smem + 16;
   const int groups = blockDim.x / LPA;
   double *fbuf_all = reinterpret_cast<double *>(img + P.img.bytes);
-  uint16_t *cand_all = reinterpret_cast<uint16_t *>(fbuf_all + (size_t)groups * 3 * (LPA + kFastSumUnroll));
+  const uint32_t fbuf_stride = rollout_fbuf_stride(LPA);
+  uint16_t *cand_all = reinterpret_cast<uint16_t *>(fbuf_all + (size_t)groups * fbuf_stride);
   const uint32_t cand_stride = rollout_cand_stride(P.n_obs);
   uint32_t *known_all = reinterpret_cast<uint32_t *>(cand_all + (size_t)groups * cand_stride);
 
@@ -269,7 +310,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   const int a = blockIdx.x * groups + group_in_block;  // local agent index
   const bool have_agent = a < P.n_agents;
   uint16_t *cand = cand_all + (size_t)group_in_block * cand_stride;
-  double *fbuf = fbuf_all + (size_t)group_in_block * 3 * (LPA + kFastSumUnroll);
+  double *fbuf = fbuf_all + (size_t)group_in_block * fbuf_stride;
   KnownBits known;
   known.w = known_all + (size_t)group_in_block * P.known_words;
 
@@ -322,12 +363,15 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   const int max_steps = keep(P.max_steps, rz);
   const bool fused = keep(P.fused_valid, rz) != 0;
   const WsParams wsp = pin_ws(P.fused_cost.ws, P.fused_cost.k_workspace, rz);
-  // latency build, one warp per agent: common steps take the straight-line path (pmaf_fast.cuh)
-  constexpr bool FAST = OCC == 1 && LPA == 32;
-  static_assert(!MULTI || (FAST && !DYNAMIC), "MULTI exists for the static latency build only");
+  // 255-register build: common steps take the straight-line path (pmaf_fast.cuh) — one warp per agent (latency
+  // shapes: fast_step, or fast_step_multi for more than 64 field obstacles), or 2 / 4 agents per warp
+  // (throughput shapes: always the chunked fast_step_multi)
+  constexpr bool FAST = (OCC == 1 && LPA >= 8) || (LPA >= 8 && LPA < 32);  // packed shapes: at every register budget
+  constexpr bool CHUNKED = MULTI || LPA < 32;
+  static_assert(!MULTI || (OCC == 1 && LPA == 32 && !DYNAMIC), "MULTI exists for the static one-warp-per-agent build only");
   if (FAST && have_agent) {  // the agent's rotation-vector row into L1 now: its first uses sit on the critical path
     const char *row = reinterpret_cast<const char *>(rot_row);
-    for (int off = g.gl * 128; off < P.n_obs * 24; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + off));
+    for (int off = g.gl * 128; off < P.n_obs * 24; off += LPA * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + off));
   }
   FastConsts fc;
   if (FAST) fc = make_fast_consts(k, type, rz);
@@ -343,7 +387,60 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   long long st_fast_cyc = 0, st_gen_cyc = 0, st_gen = 0, st_cand = 0, st_latch_cyc = 0, st_latch = 0;
 #endif
   const uint16_t *nn_table = P.img.nn_valid ? reinterpret_cast<const uint16_t *>(img + P.img.off_nn) : nullptr;
-  if constexpr (FAST && !DYNAMIC) {
+  if constexpr (FAST && LPA < 32) {
+    // Packed shapes (2 / 4 agents per warp), static and moving scenes: the rotated loop of the latency build, run
+    // by the whole warp in lockstep — the hot part of an iteration (commit of the previous step, prologue, broad
+    // phase, fast_step_packed) is executed by all 32 lanes together with warp-convergent collectives; a group
+    // whose agent has finished (or does not exist) stays in the loop predicated off until the warp's last agent
+    // is done. Only termination and rare events take a group-divergent branch.
+    v3 prev = p;
+    bool pending = false;  // a step was taken whose commit is outstanding
+    for (;;) {
+      const bool had_step = pending;  // the previous iteration took a step: commit it now
+      const v3 seg = sub3(p, prev);
+      const double zs = dot3(seg, seg);
+      const v3 goal_vec = sub3(goal, p);
+      bool pr_bad;
+      Prologue pr = step_prologue_nofallback<!DYNAMIC, false>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, had_step, k, pr_bad);
+      const StepNorms &sn = pr.sn;
+      const double path_len_before = path_len;
+      path_len += sn.seg_len;  // getPathLength term (:29), in path order; +0.0 when no step is outstanding
+      if (fused) {
+        const double w = add_workspace_cost_bf(ws_cost, p, wsp.ws, wsp.k_workspace);
+        ws_cost = had_step ? w : ws_cost;
+      }
+      st3_if(path_row + (size_t)n_path * 3, p, had_step & (g.gl == 0));
+      n_path += had_step ? 1 : 0, steps_run += had_step ? 1 : 0;
+      const bool step_on = alive & (sn.dist_goal > 0.1) & (n_path < max_steps) & !pr_bad;  // :310-311
+      prev = p;
+      pr.n_cand = broad_phase_loop_w(g, bp, env.n_obs - 1, p, cand);
+      const bool done = fast_step_packed<!DYNAMIC>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
+                                                   goal_vec, pr, p, v, min_obs, step_on, DYNAMIC ? nullptr : nn_table);
+      pending = done;
+      if (__builtin_expect(!done & alive, 0)) {  // group-divergent: termination or a rare event
+        if (pr_bad) {  // an operand outside FastMath's range: the prologue again with the IEEE built-ins
+          redo_prologue_exact<!DYNAMIC>(pr, goal_vec, v, zs, had_step, k);
+          path_len = path_len_before + sn.seg_len;
+        }
+        if (sn.dist_goal > 0.1 && n_path < max_steps) {
+          ++general_steps;
+          agent_step<!DYNAMIC, true>(g, env, obs, bp, cand, fbuf, known, type, k, init_pos, rot_row, random_row, goal_vec, pr,
+                                     p, v, min_obs PMAF_T_PASS);
+          pending = true;
+        } else {
+          alive = false;
+        }
+      }
+      if (DYNAMIC) {
+        // predictObstacles (:270-276): the CTA's shared obstacle image advances in lockstep with its agents
+        if (!__syncthreads_or(alive)) break;
+        advance_obstacles(img, P.img, env.n_obs, obs, bp);
+        __syncthreads();
+      } else if (!__any_sync(0xffffffffu, alive)) {
+        break;
+      }
+    }
+  } else if constexpr (FAST && !DYNAMIC) {
     // Latency build, static scene: the loop is rotated — the commit of the previous step (path point,
     // workspace cost, counters) shares ONE basic block with this step's prologue, and one branch decides
     // between the straight-line step and everything else (termination, closed gate, rare events).
@@ -355,7 +452,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         const double zs = dot3(seg, seg);
         const v3 goal_vec = sub3(goal, p);
         bool pr_bad;
-        Prologue pr = step_prologue_nofallback<true, !MULTI>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k, pr_bad);
+        Prologue pr = step_prologue_nofallback<true, !CHUNKED>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, pending, k, pr_bad);
         const StepNorms &sn = pr.sn;
         const double path_len_before = path_len;
         path_len += sn.seg_len;  // getPathLength term (:29), in path order; 0 while nothing is pending
@@ -376,7 +473,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         unsigned *why = nullptr;
 #endif
         bool done;
-        if constexpr (MULTI) {
+        if constexpr (CHUNKED) {
           pr.n_cand = broad_phase_loop(g, bp, env.n_obs - 1, p, cand);
           done = fast_step_multi<true>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec,
                                        pr, p, v, min_obs, step_on, nn_table);
@@ -419,7 +516,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         const v3 goal_vec = sub3(goal, p);
         bool pr_bad;
         const bool had_step = pending;  // the previous iteration took a step: commit it now
-        Prologue pr = step_prologue_nofallback<false>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, had_step, k, pr_bad);
+        Prologue pr = step_prologue_nofallback<false, !CHUNKED>(g, bp, env.n_obs - 1, cand, goal_vec, p, v, zs, had_step, k, pr_bad);
         const StepNorms &sn = pr.sn;
         const double path_len_before = path_len;
         path_len += sn.seg_len;
@@ -432,8 +529,15 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
         pending = false;
         bool step_on = (sn.dist_goal > 0.1) & (n_path < max_steps) & !pr_bad;  // :310-311
         prev = p;
-        const bool done = fast_step<false>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row,
-                                           goal_vec, pr, p, v, min_obs, nullptr, step_on);
+        bool done;
+        if constexpr (CHUNKED) {
+          pr.n_cand = broad_phase_loop(g, bp, env.n_obs - 1, p, cand);
+          done = fast_step_multi<false>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec,
+                                        pr, p, v, min_obs, step_on, nullptr);
+        } else {
+          done = fast_step<false>(g, env, obs, cand, fbuf, known, type, k, fc, init_pos, rot_row, random_row, goal_vec, pr,
+                                  p, v, min_obs, nullptr, step_on);
+        }
         if (!done) {
           if (pr_bad) {
             redo_prologue_exact<false>(pr, goal_vec, v, zs, had_step, k);

@@ -84,6 +84,16 @@ def test_lane_count_does_not_change_results(name, lanes):
     assert_bit_identical(b, a, ctx=f"{name} lanes={lanes}: ")
 
 
+@pytest.mark.parametrize("lanes", [8, 16])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_packed_shapes_match_reference_goldens(name, lanes):
+    """4 / 2 agents per warp (fast_step_packed: closed gates, ragged terminations, NaN rotation vectors, latches,
+    moving obstacles all inside one warp-convergent loop) against the goldens of the reference build, bit for bit."""
+    want = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    got = CASES[name](_planner(lanes_per_agent=lanes))
+    assert_bit_identical(got, want, ctx=f"{name} lanes={lanes}: ")
+
+
 @pytest.mark.parametrize("name", ["anchor_A8_H50", "near326_switching", "moving0", "had_nan_on_axis"])
 def test_fused_tick_equals_call_by_call(name):
     """pmaf_tick (device-resident chain) == the five CfManager calls of planCallback."""
