@@ -79,6 +79,16 @@ class ClockSampler:
         except OSError:
             pass
 
+    def wait_ready(self, timeout=8.0):
+        """nvidia-smi's start-up (driver / NVML initialisation) can stall CUDA calls of other processes for
+        milliseconds: wait for its first sample before anything is timed."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                break
+            time.sleep(0.05)
+        return self
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -238,23 +248,36 @@ def measure(env, args, sc1, steps, warmup, seeded_random=False):
         feed.step()
         return out
 
+    def timed_ticks(n):
+        ms = 0.0
+        for _ in range(n):
+            mgr.flush_l2()
+            mgr.stop_prediction()
+            mgr.timer_start()
+            tick()
+            ms += mgr.timer_stop()  # waits for the rollout this tick launched
+        return ms
+
+    mgr.set_rollout_timing(False)  # production setting: no per-kernel events, the rollout is a dependent launch
     for _ in range(max(warmup, 3)):
         tick()
     mgr.stop_prediction()
     c0 = mgr.counters()
     env.barrier()
-    dev_ms = 0.0
-    for _ in range(steps):
-        mgr.flush_l2()
-        mgr.stop_prediction()
-        mgr.timer_start()
-        tick()
-        dev_ms += mgr.timer_stop()  # waits for the rollout this tick launched
+    dev_ms = timed_ticks(steps)
     env.barrier()
     c1 = mgr.counters()
     steps_local = c1["agent_steps_total"] - c0["agent_steps_total"]
     launches = c1["kernel_launches"] - c0["kernel_launches"]
-    rollout_ms = (c1["rollout_ms_total"] - c0["rollout_ms_total"]) / steps
+    # roofline pass: the same ticks again with CUDA events around every rollout kernel (they would serialise the
+    # tick's two launches, so they stay out of the pass `value` comes from)
+    mgr.set_rollout_timing(True)
+    k0 = mgr.counters()
+    timed_ticks(steps)
+    mgr.stop_prediction()
+    k1 = mgr.counters()
+    rollout_ms = (k1["rollout_ms_total"] - k0["rollout_ms_total"]) / steps
+    steps_per_launch = (k1["agent_steps_total"] - k0["agent_steps_total"]) / steps
 
     # ---- e2e: the reference-facing calls with host buffers, wall clock ----
     # the library's C++ host loop (pmaf_dry_run: planCallback's five CfManager calls per tick through the C ABI,
@@ -265,15 +288,15 @@ def measure(env, args, sc1, steps, warmup, seeded_random=False):
     e0 = mgr.counters()
     env.barrier()
     n_feed = sc.num_obstacles - 1 if feed.active else 0
+    tick_s = []
     e2e_s, _, _, _ = mgr.dry_run(steps, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
                                  sc.k_path_len, sc.k_safe_dist, sc.k_workspace, sc.ws_limits,
-                                 feed_frequency=feed.frequency, wait_rollout=True, flush_l2=True)
+                                 feed_frequency=feed.frequency, wait_rollout=True, flush_l2=True, tick_times=tick_s)
     e1 = mgr.counters()
     e2e_steps_local = e1["agent_steps_total"] - e0["agent_steps_total"]
     (dev_ms, e2e_s, rollout_ms), (steps_all, e2e_steps_all) = env.reduce([dev_ms, e2e_s, rollout_ms],
                                                                          [steps_local, e2e_steps_local])
     O = sc.num_obstacles
-    steps_per_launch = steps_local / steps
     alg_bytes = 24.0 * steps_per_launch + 128.0 * mgr.A + 56.0 * O
     alg_flops = (40.0 * (O - 1) + 100.0) * steps_per_launch
     rec = {
@@ -286,11 +309,13 @@ def measure(env, args, sc1, steps, warmup, seeded_random=False):
                 "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) / steps,
                 "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) / steps,
                 "ms_per_step": 1e3 * e2e_s / steps,
+                "ms_per_step_median_max_rank0": [1e3 * float(np.median(tick_s)), 1e3 * float(np.max(tick_s))],
                 "api": "pmaf_dry_run (C++ host loop): per tick stop_prediction, evaluate_agents, move_real_agent, "
                        "get_next_position/velocity, reset_agents, start_prediction on host obstacle lists"},
         "gpu_launches": int(launches),
         "_kernel": {"ms": rollout_ms, "alg_bytes": alg_bytes, "alg_flops": alg_flops,
-                    "general_step_share": (c1["general_steps_total"] - c0["general_steps_total"]) / max(steps_local, 1)},
+                    "general_step_share": (c1["general_steps_total"] - c0["general_steps_total"]) / max(steps_local, 1),
+                    "timing": "CUDA events around the rollout kernel in a second pass over the same ticks"},
     }
     return rec, mgr
 
@@ -305,7 +330,8 @@ def roofline(rec, fp64_peak, peaks, peak_src, traffic):
     return {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
             "traffic": traffic, "peak_source": "measured in this run: independent DFMA chains on all SMs (pmaf_measure_fp64_peak)",
             "algorithmic_flops": k["alg_flops"], "algorithmic_flops_per_agent_step": "40*(O-1)+100 (SURVEY.md §8d)",
-            "kernel": "rollout_kernel", "kernel_ms": k["ms"], "kernel_share_of_step": k["ms"] / rec["ms_per_step"],
+            "kernel": "rollout_kernel", "kernel_ms": k["ms"], "kernel_ms_timing": k["timing"],
+            "kernel_share_of_step": k["ms"] / rec["ms_per_step"],
             "general_step_share": k["general_step_share"],
             "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                     "algorithmic_bytes": k["alg_bytes"], "peak_source": peak_src,
@@ -356,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
     parity = sharded_parity(env, args) if world > 1 else None
     if parity not in (None, "ok"):
         raise SystemExit(f"bench.py: sharded parity failed before timing: {parity}")
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank).wait_ready() if rank == 0 else None
     rec, mgr = measure(env, args, WORKLOADS[args.workload](), args.steps, args.warmup)
     fp64_peak = mgr.measure_fp64_peak()
     mgr.close()

@@ -228,6 +228,7 @@ int pmaf_get_costs(pmaf_planner *p, double *costs /* [n_agents] */);
 #define PMAF_DRY_RUN_WAIT_ROLLOUT 1
 #define PMAF_DRY_RUN_FLUSH_L2 2
 #define PMAF_DRY_RUN_PROFILE 4
+#define PMAF_DRY_RUN_TICK_TIMES 8 /* seconds must hold 7 + ticks doubles; seconds[7 + t] = wall time of tick t */
 int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_pos, const double *obs_vel, const double *obs_rad,
                  int n_feed, double feed_frequency, double delta_t, double k_goal_dist, double k_path_len,
                  double k_safe_dist, double k_workspace, const double ws_limits[6], int flags, double *seconds,
@@ -255,6 +256,10 @@ typedef struct {
                                  * instead of the straight-line one (latency build; csrc/pmaf_fast.cuh) */
 } pmaf_counters;
 int pmaf_get_counters(pmaf_planner *p, pmaf_counters *out);
+/* Rollout kernel timing (CUDA events around every rollout; last_rollout_ms / rollout_ms_total). On by default.
+ * Off: no events, and pmaf_tick's rollout starts as a programmatic dependent launch of the tick kernel (its
+ * launch latency overlaps the evaluate / real-agent step) — the production setting. */
+int pmaf_set_rollout_timing(pmaf_planner *p, int on);
 /* Developer instrumentation (libraries built with -DPMAF_FAST_STATS, all zero otherwise): how many steps
  * each reason kept off the straight-line step since create — out[0] unusable / candidate count, [1] start
  * radius threshold, [2] range flag (distance chain), [3] first detection needing the general latch,

@@ -39,6 +39,11 @@ class CfManager {
   int n_agents_ = 0;
   int n_obstacles_ = 0;
   size_t max_steps_ = 0;
+  // getPredictedPaths() is a full [agents][horizon][3] device copy; the node calls it up to 3 x agents times per
+  // tick between stopPrediction and resetEEAgents (panda_bimanual_control.cpp:341-343), so the converted paths
+  // are cached until a call that can change them
+  std::vector<std::vector<Eigen::Vector3d>> paths_cache_;
+  bool paths_cached_ = false;
 
   static void check(int rc, const char *what) {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + pmaf_last_error());
@@ -90,7 +95,8 @@ class CfManager {
     if (this != &o) {
       joinPredictionThreads();
       h_ = o.h_, device_ = o.device_, n_agents_ = o.n_agents_, n_obstacles_ = o.n_obstacles_, max_steps_ = o.max_steps_;
-      o.h_ = nullptr;
+      paths_cache_ = std::move(o.paths_cache_), paths_cached_ = o.paths_cached_;
+      o.h_ = nullptr, o.paths_cached_ = false;
     }
     return *this;
   }
@@ -103,16 +109,20 @@ class CfManager {
   pmaf_planner *nativeHandle() { return handle(); }
 
   // ---- cf_manager.h:57-68 ----
-  void startPrediction() { check(pmaf_start_prediction(handle()), "startPrediction"); }
+  void startPrediction() {
+    paths_cached_ = false;
+    check(pmaf_start_prediction(handle()), "startPrediction");
+  }
   void stopPrediction() { check(pmaf_stop_prediction(handle()), "stopPrediction"); }
   void shutdownAllAgents() {}
   void joinPredictionThreads() {
     if (h_) pmaf_destroy(h_);
-    h_ = nullptr;
+    h_ = nullptr, paths_cached_ = false;
   }
 
   // ---- cf_manager.h:69-92 ----
   std::vector<std::vector<Eigen::Vector3d>> getPredictedPaths() {
+    if (paths_cached_) return paths_cache_;
     std::vector<int> steps(n_agents_);
     check(pmaf_get_agent_summaries(handle(), steps.data(), nullptr, nullptr, nullptr, nullptr, nullptr), "getPredictedPaths");
     std::vector<double> flat((size_t)n_agents_ * max_steps_ * 3);
@@ -122,6 +132,7 @@ class CfManager {
       paths[a].reserve(steps[a]);
       for (int k = 0; k < steps[a]; ++k) paths[a].push_back(vec(&flat[((size_t)a * max_steps_ + k) * 3]));
     }
+    paths_cache_ = paths, paths_cached_ = true;
     return paths;
   }
   std::vector<double> getPredictedPathLengths() {
@@ -211,6 +222,7 @@ class CfManager {
   void setInitialEEPositions(const Eigen::Vector3d &position) { setInitialPosition(position); }
   void setInitialPosition(const Eigen::Vector3d &position) {
     const double p[3] = {position.x(), position.y(), position.z()};
+    paths_cached_ = false;
     check(pmaf_set_initial_position(handle(), p), "setInitialPosition");
   }
   void setEEAgentPosAndVels(const Eigen::Vector3d &, const Eigen::Vector3d &) { unsupported("setEEAgentPosAndVels"); }
@@ -218,6 +230,7 @@ class CfManager {
                      const std::vector<Obstacle> &obstacles) {
     const Flat o(obstacles);
     const double p[3] = {position.x(), position.y(), position.z()}, v[3] = {velocity.x(), velocity.y(), velocity.z()};
+    paths_cached_ = false;
     check(pmaf_reset_agents(handle(), p, v, o.n(), o.pos.data(), o.vel.data(), o.rad.data()), "resetEEAgents");
   }
 

@@ -82,6 +82,7 @@ struct pmaf_planner {
   int roll_slot = 0;
   cudaEvent_t ev_d2h = nullptr, ev_stage = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   bool upload_dedup = true;
+  bool time_rollouts = true;  // CUDA events around every rollout kernel (pmaf_set_rollout_timing)
   bool initialized = false;
   // shard
   int n_global = 0, first_agent = 0, rank = 0, world = 1;
@@ -132,6 +133,10 @@ struct pmaf_planner {
   bool fused_valid = false;
   ObstacleImage img{};
   float margin = 1e-3f;
+  double margin_scale_static = 0.0;  // largest |coordinate| among goal, start, obstacles (broad_phase_margin)
+  bool image_current = false;        // the staging image matches the agents' obstacle copy, layout and margin
+  bool live_changed = false;         // upload_live sent a new list since the image was built
+  DevBuf<uint32_t> known_bits, known_keep;  // packed real-agent flags for the rollout's in-prologue reset
   // rollout bookkeeping
   bool rollout_pending = false;
   bool obstacles_advanced = false;  // a dynamic rollout advanced the agents' obstacle copies
@@ -181,6 +186,8 @@ static PlannerDev make_dev(const pmaf_planner *p) {
   d.step_counter = p->step_counter.p;
   d.section_cycles = p->section_cycles.p;
   d.runtime_zero = p->runtime_zero.p;
+  d.reset_in_prologue = 0, d.reset_real = p->real.p;
+  d.reset_known_bits = p->known_bits.p, d.reset_known_keep = p->known_keep.p;
   return d;
 }
 
@@ -220,15 +227,29 @@ static bool any_nonzero(const std::vector<double> &v) {
   return false;
 }
 
-static float broad_phase_margin(const pmaf_planner *p, const double *pos) {
+// Broad-phase safety margin (metres): dominates the fp32 rounding of coordinates up to `s` in magnitude.
+// s = the largest coordinate the rollout can meet: goal, start, obstacles (static part, recomputed when the
+// obstacle list changes) and the real agent's position, plus the farthest an agent / obstacle can travel.
+static void refresh_margin_scale(pmaf_planner *p) {
   double s = 0.0;
-  for (int i = 0; i < 3; ++i) s = std::max({s, std::fabs(p->goal[i]), std::fabs(pos[i]), std::fabs(p->mgr_init_pos[i])});
-  double vmax_obs = 0.0;
+  for (int i = 0; i < 3; ++i) s = std::max({s, std::fabs(p->goal[i]), std::fabs(p->mgr_init_pos[i])});
   for (double x : p->h_obs_pos) s = std::max(s, std::fabs(x));
+  double vmax_obs = 0.0;
   for (double x : p->h_obs_vel) vmax_obs = std::max(vmax_obs, std::fabs(x));
   s += (p->vel_max + vmax_obs * 1.7320508) * p->pred_dt * p->H;
+  p->margin_scale_static = s;
+}
+static float broad_phase_margin(const pmaf_planner *p, const double *pos) {
+  double s = p->margin_scale_static;
+  for (int i = 0; i < 3; ++i) s = std::max(s, std::fabs(pos[i]) + p->vel_max * p->pred_dt * p->H);
   if (!std::isfinite(s)) s = 1e6;
   return (float)(1e-3 + 4e-6 * s);
+}
+// the margin only ever grows between two inits (a larger margin is always safe), so that the staging image of
+// a static scene stays valid from tick to tick
+static void update_margin(pmaf_planner *p, const double *pos) {
+  const float m = broad_phase_margin(p, pos);
+  if (m > p->margin) p->margin = m, p->image_current = false;
 }
 
 // wait until the pinned H2D staging buffer may be overwritten
@@ -500,6 +521,7 @@ extern "C" int pmaf_destroy(pmaf_planner *p) {
         &p->scratch, &p->real_path_out})
     b->release();
   p->l2_scratch.release();
+  p->known_bits.release(), p->known_keep.release();
   p->section_cycles.release();
   p->runtime_zero.release();
   p->n_path.release(), p->reached.release(), p->known.release(), p->image.release(), p->real_known.release();
@@ -556,6 +578,21 @@ static int launch(pmaf_planner *p, K kernel, dim3 grid, dim3 block, size_t smem,
   p->ctr.kernel_launches++;
   return 0;
 }
+// Programmatic dependent launch: the grid may start while its predecessor in the stream (which executes
+// griddepcontrol.launch_dependents) is still running; the kernel itself waits (griddepcontrol.wait) before it
+// touches anything the predecessor writes. Hides the launch latency of the rollout behind tick_kernel.
+template <class... KArgs, class... Args>
+static int launch_dependent(pmaf_planner *p, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = p->stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr, cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+  p->ctr.kernel_launches++;
+  return 0;
+}
 
 // (re)build the staging image and, optionally, reset the agents
 static int launch_reset(pmaf_planner *p, bool do_agents, bool from_real, const double *dev_pos_vel, int n_update,
@@ -572,6 +609,7 @@ static int launch_reset(pmaf_planner *p, bool do_agents, bool from_real, const d
   r.agent_blocks = do_agents ? (p->A + block - 1) / block : 1;
   // nearest-neighbour table: one warp per obstacle row, spread over extra blocks (they overlap block 0)
   const int nn_blocks = p->img.nn_valid ? std::min(64, (p->O - 1 + 3) / 4) : 0;
+  p->image_current = true, p->live_changed = false;
   return launch(p, reset_kernel, dim3(r.agent_blocks + nn_blocks), dim3(block), 0, d, r);
 }
 
@@ -639,6 +677,8 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
   CU(p->live_pos.resize(O * 7));  // pos | vel | rad in one block: one upload per call
   p->live_vel.alias(p->live_pos.p + 3 * O, 3 * O), p->live_rad.alias(p->live_pos.p + 6 * O, O);
   CU(p->real_known.resize(O));
+  CU(p->known_bits.resize(p->known_words));
+  CU(p->known_keep.resize(p->known_words));
   CU(p->real_rot.resize(O * 3));
   CU(p->rec.resize(argmin_record_bytes((int)O)));
   CU(p->rec_all.resize(argmin_record_bytes((int)O) * (size_t)p->world));
@@ -726,7 +766,9 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
   p->img = layout_image((int)O, any_nonzero(p->h_obs_vel));
   p->img.nn_valid = wants_nn_table(p, p->img);
   CU(p->image.resize(p->img.bytes));
+  refresh_margin_scale(p);
   p->margin = broad_phase_margin(p, p->mgr_init_pos);
+  p->image_current = false, p->live_changed = false;
 
   // agents constructed at the manager's init_pos_ (cf_manager.cpp:70-104)
   {
@@ -806,7 +848,7 @@ extern "C" int pmaf_set_real_position(pmaf_planner *p, const double pos[3]) {
 }
 
 template <int LPA>
-static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, bool dynamic) {
+static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, bool dynamic, bool dependent) {
   const int groups = block / LPA;
   const int grid = (p->A + groups - 1) / groups;
   const size_t smem = rollout_smem_bytes(p->img, groups, LPA, p->known_words);
@@ -832,6 +874,7 @@ static int launch_rollout_lpa(pmaf_planner *p, const PlannerDev &d, int block, b
   p->ctr.occupancy_build = occ;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p->ctr.lanes_per_agent = LPA, p->ctr.block_threads = block, p->ctr.grid_blocks = grid, p->ctr.smem_bytes = (int)smem;
+  if (dependent) return launch_dependent(p, kern, dim3(grid), dim3(block), smem, d);
   return launch(p, kern, dim3(grid), dim3(block), smem, d);
 }
 
@@ -855,26 +898,37 @@ static void pick_rollout_shape(const pmaf_planner *p, int &lpa, int &block) {
   if (block < lpa) block = lpa;
 }
 
-static int launch_rollout(pmaf_planner *p) {
+static int launch_rollout(pmaf_planner *p, bool reset_in_prologue = false) {
   PlannerDev d = make_dev(p);
+  d.reset_in_prologue = reset_in_prologue ? 1 : 0;
   int lpa, block;
   pick_rollout_shape(p, lpa, block);
-  CU(cudaMemsetAsync(p->step_counter.p, 0, sizeof(unsigned long long), p->stream));
-  p->roll_slot ^= 1;  // the slot used two rollouts ago: finished long before this point in the stream
-  if (int rc = harvest_timing(p, p->roll_slot, true)) return rc;
-  CU(cudaEventRecord(p->ev_roll[p->roll_slot][0], p->stream));
+  // per-rollout step counter: zeroed by tick_kernel on the fused path (one stream operation less per tick)
+  if (!reset_in_prologue) CU(cudaMemsetAsync(p->step_counter.p, 0, sizeof(unsigned long long), p->stream));
+  const bool timed = p->time_rollouts;
+  // untimed rollouts on the fused path start as programmatic dependents of tick_kernel (an event record in
+  // between would serialise the two again)
+  const bool dependent = reset_in_prologue && !timed;
+  if (timed) {
+    p->roll_slot ^= 1;  // the slot used two rollouts ago: finished long before this point in the stream
+    if (int rc = harvest_timing(p, p->roll_slot, true)) return rc;
+    CU(cudaEventRecord(p->ev_roll[p->roll_slot][0], p->stream));
+  }
   int rc;
   const bool dyn = p->img.dynamic != 0;
   switch (lpa) {
-    case 4: rc = launch_rollout_lpa<4>(p, d, block, dyn); break;
-    case 8: rc = launch_rollout_lpa<8>(p, d, block, dyn); break;
-    case 16: rc = launch_rollout_lpa<16>(p, d, block, dyn); break;
-    default: rc = launch_rollout_lpa<32>(p, d, block, dyn); break;
+    case 4: rc = launch_rollout_lpa<4>(p, d, block, dyn, dependent); break;
+    case 8: rc = launch_rollout_lpa<8>(p, d, block, dyn, dependent); break;
+    case 16: rc = launch_rollout_lpa<16>(p, d, block, dyn, dependent); break;
+    default: rc = launch_rollout_lpa<32>(p, d, block, dyn, dependent); break;
   }
   if (rc) return rc;
-  CU(cudaEventRecord(p->ev_roll[p->roll_slot][1], p->stream));
+  if (timed) {
+    CU(cudaEventRecord(p->ev_roll[p->roll_slot][1], p->stream));
+    p->roll_timing[p->roll_slot] = true;
+  }
   p->ctr.rollouts++;
-  p->rollout_pending = true, p->roll_timing[p->roll_slot] = true;
+  p->rollout_pending = true;
   if (dyn) p->obstacles_advanced = true;
   p->agents_touched = false;
   return 0;
@@ -978,6 +1032,7 @@ static int upload_live(pmaf_planner *p, int n_obs, const double *obs_pos, const 
                     memcmp(last.data() + 3 * n, obs_vel, 3 * n * sizeof(double)) == 0 &&
                     memcmp(last.data() + 6 * n, obs_rad, n * sizeof(double)) == 0;
   if (same) return 0;
+  p->live_changed = true;
   last.resize(7 * n);
   memcpy(last.data(), obs_pos, 3 * n * sizeof(double));
   memcpy(last.data() + 3 * n, obs_vel, 3 * n * sizeof(double));
@@ -994,17 +1049,10 @@ static int upload_live(pmaf_planner *p, int n_obs, const double *obs_pos, const 
   return stage_release(p);
 }
 
+static RealArgs make_real_args(pmaf_planner *p, int n_obs, double delta_t, int steps, int agent_id_global);
 static int launch_real(pmaf_planner *p, int n_obs, double delta_t, int steps, int agent_id_global) {
   PlannerDev d = make_dev(p);
-  RealArgs r{};
-  r.real = p->real.p, r.known = p->real_known.p, r.rot = p->real_rot.p, r.best = p->best.p;
-  r.best_random = p->best_random.p;
-  r.obs_pos = p->live_pos.p, r.obs_vel = p->live_vel.p, r.obs_rad = p->live_rad.p, r.n_obs = n_obs;
-  r.delta_t = delta_t, r.steps = steps, r.agent_id = agent_id_global, r.eval = p->eval.p;
-  r.path_out = p->real_path_out.p;
-  for (int i = 0; i < 3; ++i) r.goal[i] = p->goal[i];
-  r.host = p->h_out_dev, r.ticket = ++p->ticket;
-  p->ctr.d2h_bytes += sizeof(RealState) + (size_t)steps * 3 * sizeof(double);  // stored by the kernel into the host block
+  const RealArgs r = make_real_args(p, n_obs, delta_t, steps, agent_id_global);
   return launch(p, real_agent_kernel, dim3(1), dim3(32), 0, d, r);
 }
 
@@ -1040,7 +1088,9 @@ static int refresh_obstacle_copy(pmaf_planner *p, int n_obs, const double *obs_p
   im.nn_valid = wants_nn_table(p, im);
   if (im.bytes != p->img.bytes) CU(p->image.resize(im.bytes));
   p->img = im;
-  p->margin = broad_phase_margin(p, pos);
+  refresh_margin_scale(p);
+  update_margin(p, pos);
+  p->image_current = false;
   return 0;
 }
 
@@ -1073,6 +1123,21 @@ extern "C" int pmaf_reset_agents(pmaf_planner *p, const double pos[3], const dou
   return 0;
 }
 
+// RealArgs of one launch (shared by real_agent_kernel and tick_kernel)
+static RealArgs make_real_args(pmaf_planner *p, int n_obs, double delta_t, int steps, int agent_id_global) {
+  RealArgs r{};
+  r.real = p->real.p, r.known = p->real_known.p, r.rot = p->real_rot.p, r.best = p->best.p;
+  r.best_random = p->best_random.p;
+  r.obs_pos = p->live_pos.p, r.obs_vel = p->live_vel.p, r.obs_rad = p->live_rad.p, r.n_obs = n_obs;
+  r.delta_t = delta_t, r.steps = steps, r.agent_id = agent_id_global, r.eval = p->eval.p;
+  r.path_out = p->real_path_out.p;
+  for (int i = 0; i < 3; ++i) r.goal[i] = p->goal[i];
+  r.host = p->h_out_dev, r.ticket = ++p->ticket;
+  r.pub_eval = nullptr, r.pub_best = nullptr;
+  p->ctr.d2h_bytes += sizeof(RealState) + (size_t)steps * 3 * sizeof(double);  // stored by the kernel into the host block
+  return r;
+}
+
 extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs, const double *obs_pos,
                          const double *obs_vel, const double *obs_rad, double delta_t, double k_goal_dist,
                          double k_path_len, double k_safe_dist, double k_workspace, const double ws_limits[6],
@@ -1088,19 +1153,67 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   if (int rc = harvest_timing(p, p->roll_slot, false)) return rc;
   if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
   const CostParams C = make_cost(k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits);
-  if (int rc = launch_evaluate(p, C)) return rc;
-  if (int rc = launch_real(p, n_obs, delta_t, 1, -1)) return rc;
-  if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, p->h_real.pos)) return rc;
+  // Two launches per tick: tick_kernel (evaluateAgents [+ best-agent exchange], moveRealEEAgent, obstacle image /
+  // known flags for the reset) and the rollout, whose prologue is resetEEAgents.
+  PlannerDev d = make_dev(p);
+  if (!(p->fused_valid && p->have_cost && same_cost(C, p->last_cost))) {
+    if (int rc = launch(p, workspace_cost_kernel, dim3((p->A + 127) / 128), dim3(128), 0, d, C)) return rc;
+  }
+  p->last_cost = C, p->have_cost = true;
+  if (p->live_changed || !p->image_current) {
+    if (int rc = refresh_obstacle_copy(p, n_obs, obs_pos, obs_vel, p->h_real.pos)) return rc;
+  } else {
+    update_margin(p, p->h_real.pos);
+  }
+  d = make_dev(p);  // the image layout may have changed
+  TickArgs T{};
+  T.best = p->best.p, T.best_random = p->best_random.p, T.rec = reinterpret_cast<ArgminRecord *>(p->rec.p);
+  T.eval = p->eval.p, T.host = p->h_out_dev, T.world = p->world;
+  T.p2p_status = (int *)&p->h_out_dev->p2p_fail;
+  T.known_bits = p->known_bits.p, T.known_keep = p->known_keep.p;
+  T.rebuild_image = p->image_current ? 0 : 1;
+  T.rebuild_nn = (T.rebuild_image && p->img.nn_valid) ? 1 : 0;
+  const bool copy_eval = p->world > 1 && !p->p2p_ready;  // the NCCL path's selection does not write the host block
+  if (p->world == 1) {
+    T.eval_mode = 0;
+  } else if (p->p2p_ready) {
+    REQUIRE(p->p2p_rank == p->rank && p->p2p_world == p->world, PMAF_ERR_STATE,
+            "peer-memory exchange was set up for rank %d of %d, the shard is rank %d of %d", p->p2p_rank, p->p2p_world,
+            p->rank, p->world);
+    T.eval_mode = 1;
+    for (int r = 0; r < p->world; ++r) T.xchg.peers[r] = p->peer_xchg[r];
+    T.xchg.rank = p->rank, T.xchg.world = p->world, T.xchg.seq = ++p->xseq, T.xchg.stride = p2p_slot_stride();
+    p->ctr.collectives++;
+  } else {
+    REQUIRE(p->nccl != nullptr, PMAF_ERR_STATE, "sharded planner without an exchange (pmaf_nccl_init or pmaf_p2p_import)");
+    const int threads = p->A >= 1024 ? 1024 : std::max(32, ((p->A + 31) / 32) * 32);
+    if (int rc = launch(p, evaluate_kernel, dim3(1), dim3(threads), 0, d, C, p->best.p, p->best_random.p, T.rec, p->eval.p,
+                        0, (HostOut *)nullptr, 0ull))
+      return rc;
+    NC(g_nccl.AllGather(p->rec.p, p->rec_all.p, argmin_record_bytes(p->O), ncclChar, (ncclComm_t)p->nccl, p->stream));
+    p->ctr.collectives++;
+    T.eval_mode = 2, T.rec_all = p->rec_all.p;
+  }
+  T.eval_ticket = ++p->ticket;
+  p->ctr.d2h_bytes += sizeof(EvalResult) + sizeof(DeviceBest);
+  RealArgs R = make_real_args(p, n_obs, delta_t, 1, -1);
+  if (!copy_eval) R.pub_eval = p->eval.p, R.pub_best = p->best.p;  // published with the real agent's state
+  ResetArgs S{};
+  S.real = p->real.p, S.from_real = 1, S.n_obs_update = n_obs, S.new_pos = p->live_pos.p, S.new_vel = p->live_vel.p;
+  S.obs_pos = p->obs_pos.p, S.obs_vel = p->obs_vel.p, S.obs_rad = p->obs_rad.p, S.real_known = p->real_known.p;
+  S.image = p->image.p, S.margin = p->margin;
+  // one warp for the real agent, the rest for the costs / the image (at least one more warp)
+  const int threads = std::min(1024, std::max(64, ((p->A + 31) / 32) * 32 + 32));
+  if (int rc = launch(p, tick_kernel, dim3(1), dim3(threads), 0, d, C, T, R, S)) return rc;
+  p->image_current = true, p->live_changed = false;
   p->fused_valid = true;
-  if (int rc = launch_reset(p, true, true, nullptr, n_obs, p->live_pos.p, p->live_vel.p, true, true)) return rc;
-  const unsigned long long real_ticket = p->ticket;  // launch_real published last
-  const bool copy_eval = p->world > 1 && !p->p2p_ready;
-  if (copy_eval) {  // the NCCL path's selection kernel does not write the host block
+  const unsigned long long real_ticket = p->ticket;  // the real agent publishes last
+  if (copy_eval) {
     if (int rc = d2h(p, &p->h_out->eval, p->eval.p, sizeof(EvalResult) + sizeof(DeviceBest))) return rc;
     CU(cudaEventRecord(p->ev_d2h, p->stream));
   }
   p->obstacles_advanced = false;
-  if (int rc = launch_rollout(p)) return rc;
+  if (int rc = launch_rollout(p, true)) return rc;
   if (copy_eval) CU(cudaEventSynchronize(p->ev_d2h));
   if (int rc = wait_ticket(p, 1, real_ticket)) return rc;
   REQUIRE(!p->h_out->p2p_fail, PMAF_ERR_NCCL, "best-agent exchange: a peer's record never arrived");
@@ -1127,7 +1240,8 @@ extern "C" int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_p
   REQUIRE(ticks >= 0 && obs_pos && obs_vel && obs_rad && ws_limits && n_feed >= 0 && n_feed <= n_obs, PMAF_ERR_ARG,
           "pmaf_dry_run: bad argument");
   double total = 0.0;
-  REQUIRE(!(flags & PMAF_DRY_RUN_PROFILE) || seconds, PMAF_ERR_ARG, "pmaf_dry_run: PMAF_DRY_RUN_PROFILE needs seconds[7]");
+  REQUIRE(!(flags & (PMAF_DRY_RUN_PROFILE | PMAF_DRY_RUN_TICK_TIMES)) || seconds, PMAF_ERR_ARG,
+          "pmaf_dry_run: PMAF_DRY_RUN_PROFILE needs seconds[7], PMAF_DRY_RUN_TICK_TIMES seconds[7 + ticks]");
   if (flags & PMAF_DRY_RUN_PROFILE)
     for (int k = 1; k < 7; ++k) seconds[k] = 0.0;
   for (int t = 0; t < ticks; ++t) {
@@ -1169,7 +1283,9 @@ extern "C" int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_p
     }
     lap(5);
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    total += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    const double tick_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    total += tick_s;
+    if (flags & PMAF_DRY_RUN_TICK_TIMES) seconds[7 + t] = tick_s;
     if (best) best[t] = b;
     for (int i = 0; i < 3; ++i) {
       if (next_pos) next_pos[3 * t + i] = pos[i];
@@ -1386,6 +1502,13 @@ extern "C" int pmaf_set_tuning(pmaf_planner *p, int lanes_per_agent, int block_t
   REQUIRE(occupancy == 0 || occupancy == 1 || occupancy == 3 || occupancy == 4, PMAF_ERR_ARG,
           "pmaf_set_tuning: occupancy must be 0 (auto), 1, 3 or 4");
   p->tune_lpa = lanes_per_agent, p->tune_block = block_threads, p->tune_occ = occupancy;
+  return 0;
+}
+
+extern "C" int pmaf_set_rollout_timing(pmaf_planner *p, int on) {
+  ENTER(p);
+  if (int rc = finish_rollout(p)) return rc;
+  p->time_rollouts = on != 0;
   return 0;
 }
 

@@ -151,6 +151,11 @@ struct PlannerDev {  // kernel argument, passed by value
   unsigned long long *step_counter;  // [0] executed integration steps of this rollout, [1] running total
   long long *section_cycles;         // [64][12] per-section cycle counters (PMAF_SECTION_TIMERS builds)
   const unsigned *runtime_zero;      // one word holding 0 (see keep() in pmaf_math.cuh)
+  // fused tick: resetEEAgents (cf_manager.cpp:246-255) happens in the rollout's prologue, from the real agent's
+  // state and packed known flags that tick_kernel left behind — no separate pass over the agents
+  int reset_in_prologue;
+  const RealState *reset_real;
+  const uint32_t *reset_known_bits, *reset_known_keep;  // [known_words]
 };
 
 // ---- small PTX wrappers (TMA bulk copy + mbarrier) ---------------------------------------------------
@@ -188,6 +193,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
     if (spins > (1u << 26)) __trap();
   }
+}
+// prefetch [ptr, ptr + bytes) into L2, one 128-byte line per participating thread and round
+__device__ __forceinline__ void prefetch_l2(const void *ptr, size_t bytes, int tid, int nthreads) {
+  const char *c = reinterpret_cast<const char *>(ptr);
+  for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;

@@ -548,6 +548,12 @@ PMAF_HD v3 clamp_velocity(v3 v, double vel_max) {
   return n > vel_max ? mul3(v, vel_max / n) : v;
 }
 
+// the same through the out-of-line IEEE operations (once per rollout, in the kernel's prologue)
+PMAF_HD v3 clamp_velocity_cold(v3 v, double vel_max) {
+  const double n = cold_sqrt(dot3(v, v));
+  return n > vel_max ? mul3(v, cold_div(vel_max, n)) : v;
+}
+
 // workspace term of one path point, CfManager::evaluateAgents cf_manager.cpp:302-323
 // ws = [x+, x-, y+, y-, z+, z-]
 struct WsParams {

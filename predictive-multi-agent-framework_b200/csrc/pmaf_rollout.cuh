@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
     fence_barrier_init();
   }
   __syncthreads();
+  // programmatic dependent launch (pmaf_tick): everything above overlapped the tail of tick_kernel; nothing it
+  // writes (obstacle image, real agent, known flags) is touched before this point. A no-op otherwise.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, P.img.bytes);
     tma_bulk_g2s(img, P.image, P.img.bytes, bar);
@@ -322,17 +325,31 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   double *rot_row = nullptr;
   const double *random_row = nullptr;
   if (have_agent) {
-    p = ld3(P.cur_pos + 3 * a);
-    v = ld3(P.vel + 3 * a);
     init_pos = ld3(P.init_pos + 3 * a);
-    min_obs = P.min_obs_dist[a];
-    path_len = P.path_len[a];
-    ws_cost = P.ws_cost[a];
-    n_path = P.n_path[a];
     type = agent_type_of_index(P.first_agent + a);
     rot_row = P.rot + (size_t)a * P.n_obs * 3;
     random_row = P.random_vecs + (size_t)a * P.n_obs * 3;
-    for (int w = g.gl; w < P.known_words; w += LPA) known.w[w] = P.known[(size_t)a * P.known_words + w];
+    if (P.reset_in_prologue) {
+      // resetEEAgents (cf_manager.cpp:246-255) for this agent, in registers: setPosition (path := [pos]),
+      // setVelocity (clamped, cf_agent.cpp:54-61), setObstacles' known flags (:63-70), resetMinObsDist
+      p = ld3(P.reset_real->pos);
+      v = clamp_velocity_cold(ld3(P.reset_real->vel), P.vel_max);
+      min_obs = P.shell;
+      path_len = 0.0;
+      ws_cost = P.fused_valid ? add_workspace_cost(0.0, p, P.fused_cost.ws, P.fused_cost.k_workspace) : 0.0;
+      n_path = 1;
+      if (g.gl == 0) st3(P.paths + (size_t)a * P.max_steps * 3, p);
+      for (int w = g.gl; w < P.known_words; w += LPA)
+        known.w[w] = (P.known[(size_t)a * P.known_words + w] & P.reset_known_keep[w]) | P.reset_known_bits[w];
+    } else {
+      p = ld3(P.cur_pos + 3 * a);
+      v = ld3(P.vel + 3 * a);
+      min_obs = P.min_obs_dist[a];
+      path_len = P.path_len[a];
+      ws_cost = P.ws_cost[a];
+      n_path = P.n_path[a];
+      for (int w = g.gl; w < P.known_words; w += LPA) known.w[w] = P.known[(size_t)a * P.known_words + w];
+    }
   }
   g.sync();
   mbar_wait(bar, 0);
@@ -688,60 +705,70 @@ struct ResetObstacles {
   PMAF_HDT v3 pos(int i) const { return i < n_update ? ld3(new_pos + 3 * i) : ld3(old_pos + 3 * i); }
 };
 
+// the staging image of the obstacle set (ObstacleImage), rebuilt by `nthreads` threads of one CTA
+__device__ __forceinline__ void build_obstacle_image(const PlannerDev &P, const ResetArgs &R, int tid, int nthreads) {
+  double *px = reinterpret_cast<double *>(R.image + P.img.off_px);
+  double *py = reinterpret_cast<double *>(R.image + P.img.off_py);
+  double *pz = reinterpret_cast<double *>(R.image + P.img.off_pz);
+  double *rs = reinterpret_cast<double *>(R.image + P.img.off_rs);
+  float4 *bp = reinterpret_cast<float4 *>(R.image + P.img.off_bp);
+  for (int i = tid; i < P.n_obs; i += nthreads) {
+    v3 op, ov;
+    if (i < R.n_obs_update) {
+      op = ld3(R.new_pos + 3 * i), ov = ld3(R.new_vel + 3 * i);
+      st3(R.obs_pos + 3 * i, op), st3(R.obs_vel + 3 * i, ov);
+    } else {
+      op = ld3(R.obs_pos + 3 * i), ov = ld3(R.obs_vel + 3 * i);
+    }
+    const double rsum = P.rad + R.obs_rad[i];
+    px[i] = op.x, py[i] = op.y, pz[i] = op.z, rs[i] = rsum;
+    if (P.img.dynamic) {
+      reinterpret_cast<double *>(R.image + P.img.off_vx)[i] = ov.x;
+      reinterpret_cast<double *>(R.image + P.img.off_vy)[i] = ov.y;
+      reinterpret_cast<double *>(R.image + P.img.off_vz)[i] = ov.z;
+      reinterpret_cast<double *>(R.image + P.img.off_dx)[i] = ov.x * P.pred_dt;  // getVelocity() * delta_t (:273)
+      reinterpret_cast<double *>(R.image + P.img.off_dy)[i] = ov.y * P.pred_dt;
+      reinterpret_cast<double *>(R.image + P.img.off_dz)[i] = ov.z * P.pred_dt;
+    }
+    bp[i] = broad_phase_record(op, P.shell, rsum, R.margin);
+  }
+}
+// nearest-neighbour table of a static scene (ObstacleImage::off_nn): warp `warp` of `warps` takes every warps-th row
+__device__ __forceinline__ void build_nn_table(const PlannerDev &P, const ResetArgs &R, int warp, int warps) {
+  const Group<32> g;
+  ResetObstacles obs;
+  obs.new_pos = R.new_pos, obs.old_pos = R.obs_pos, obs.n_update = R.n_obs_update;
+  uint16_t *nn = reinterpret_cast<uint16_t *>(R.image + P.img.off_nn);
+  const int n_field = P.n_obs - 1;
+  for (int row = warp; row < n_field; row += warps) {
+    const int found = nearest_other_obstacle(g, obs, n_field, row);
+    if (g.gl == 0) nn[row] = (uint16_t)found;
+  }
+}
+// the real agent's known flags as bit words: `bits` for the obstacles of the passed list, `keep` = the bits of the
+// agent's own word that survive (setObstacles only touches the obstacles of the passed list, cf_agent.cpp:63-70)
+__device__ __forceinline__ void pack_known_word(const unsigned char *real_known, int n_update, int w, uint32_t &bits,
+                                                uint32_t &keep) {
+  bits = 0, keep = 0;
+  for (int b = 0; b < 32; ++b) {
+    const int i = w * 32 + b;
+    if (i < n_update) bits |= (uint32_t)(real_known[i] != 0) << b;
+    else keep |= 1u << b;
+  }
+}
+
 // grid: ceil(A / blockDim) blocks (1 block when !do_agents); block 0 also rebuilds the staging image.
 __global__ void __launch_bounds__(128) reset_kernel(const PlannerDev P, const ResetArgs R) {
   __shared__ uint32_t s_bits[kMaxObstacles / 32], s_keep[kMaxObstacles / 32];
   if ((int)blockIdx.x >= R.agent_blocks) {  // nearest-neighbour table of a static scene (ObstacleImage::off_nn)
-    const Group<32> g;
-    ResetObstacles obs;
-    obs.new_pos = R.new_pos, obs.old_pos = R.obs_pos, obs.n_update = R.n_obs_update;
-    uint16_t *nn = reinterpret_cast<uint16_t *>(R.image + P.img.off_nn);
-    const int n_field = P.n_obs - 1;
-    const int warps = (gridDim.x - R.agent_blocks) * (blockDim.x / 32);
-    for (int row = (blockIdx.x - R.agent_blocks) * (blockDim.x / 32) + threadIdx.x / 32; row < n_field; row += warps) {
-      const int found = nearest_other_obstacle(g, obs, n_field, row);
-      if (g.gl == 0) nn[row] = (uint16_t)found;
-    }
+    build_nn_table(P, R, (blockIdx.x - R.agent_blocks) * (blockDim.x / 32) + threadIdx.x / 32,
+                   (gridDim.x - R.agent_blocks) * (blockDim.x / 32));
     return;
   }
-  if (blockIdx.x == 0) {
-    double *px = reinterpret_cast<double *>(R.image + P.img.off_px);
-    double *py = reinterpret_cast<double *>(R.image + P.img.off_py);
-    double *pz = reinterpret_cast<double *>(R.image + P.img.off_pz);
-    double *rs = reinterpret_cast<double *>(R.image + P.img.off_rs);
-    float4 *bp = reinterpret_cast<float4 *>(R.image + P.img.off_bp);
-    for (int i = threadIdx.x; i < P.n_obs; i += blockDim.x) {
-      v3 op, ov;
-      if (i < R.n_obs_update) {
-        op = ld3(R.new_pos + 3 * i), ov = ld3(R.new_vel + 3 * i);
-        st3(R.obs_pos + 3 * i, op), st3(R.obs_vel + 3 * i, ov);
-      } else {
-        op = ld3(R.obs_pos + 3 * i), ov = ld3(R.obs_vel + 3 * i);
-      }
-      const double rsum = P.rad + R.obs_rad[i];
-      px[i] = op.x, py[i] = op.y, pz[i] = op.z, rs[i] = rsum;
-      if (P.img.dynamic) {
-        reinterpret_cast<double *>(R.image + P.img.off_vx)[i] = ov.x;
-        reinterpret_cast<double *>(R.image + P.img.off_vy)[i] = ov.y;
-        reinterpret_cast<double *>(R.image + P.img.off_vz)[i] = ov.z;
-        reinterpret_cast<double *>(R.image + P.img.off_dx)[i] = ov.x * P.pred_dt;  // getVelocity() * delta_t (:273)
-        reinterpret_cast<double *>(R.image + P.img.off_dy)[i] = ov.y * P.pred_dt;
-        reinterpret_cast<double *>(R.image + P.img.off_dz)[i] = ov.z * P.pred_dt;
-      }
-      bp[i] = broad_phase_record(op, P.shell, rsum, R.margin);
-    }
-  }
+  if (blockIdx.x == 0) build_obstacle_image(P, R, threadIdx.x, blockDim.x);
   if (!R.do_agents) return;
   if (R.set_known) {  // pack the real agent's flags once per block
-    for (int w = threadIdx.x; w < P.known_words; w += blockDim.x) {
-      uint32_t bits = 0, keep = 0;
-      for (int b = 0; b < 32; ++b) {
-        const int i = w * 32 + b;
-        if (i < R.n_obs_update) bits |= (uint32_t)(R.real_known[i] != 0) << b;
-        else keep |= 1u << b;  // setObstacles only touches the obstacles of the passed list
-      }
-      s_bits[w] = bits, s_keep[w] = keep;
-    }
+    for (int w = threadIdx.x; w < P.known_words; w += blockDim.x) pack_known_word(R.real_known, R.n_obs_update, w, s_bits[w], s_keep[w]);
     __syncthreads();
   }
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -794,9 +821,9 @@ __host__ __device__ inline size_t argmin_record_bytes(int n_obs) {
 
 // single block: per-agent costs, serial-order argmin (strict <, lowest index), then — unsharded —
 // hysteresis and incumbent update.
-__global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, const CostParams C, DeviceBest *best,
-                                                        double *best_random, ArgminRecord *rec, EvalResult *out,
-                                                        int finalize, HostOut *host, unsigned long long ticket) {
+__device__ __forceinline__ void evaluate_body(const PlannerDev &P, const CostParams &C, DeviceBest *best,
+                                              double *best_random, ArgminRecord *rec, EvalResult *out, int finalize,
+                                              HostOut *host, unsigned long long ticket) {
   __shared__ double s_cost[32];
   __shared__ int s_idx[32];
   const v3 goal = ld3(P.goal);
@@ -880,6 +907,11 @@ __global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, cons
     }
   }
 }
+__global__ void __launch_bounds__(1024) evaluate_kernel(const PlannerDev P, const CostParams C, DeviceBest *best,
+                                                        double *best_random, ArgminRecord *rec, EvalResult *out,
+                                                        int finalize, HostOut *host, unsigned long long ticket) {
+  evaluate_body(P, C, best, best_random, rec, out, finalize, host, ticket);
+}
 
 // Sharded planners: after ONE all-gather of the per-rank records every rank repeats the reference's
 // serial scan over the ranks in order (ranks own contiguous ascending agent blocks, so "lowest index
@@ -947,9 +979,10 @@ __host__ __device__ inline size_t p2p_flags_offset() { return 2 * (size_t)kP2pMa
 __host__ __device__ inline size_t p2p_block_bytes() { return p2p_flags_offset() + 2 * kP2pMaxWorld * sizeof(unsigned long long); }
 
 // out_status: 0 ok, 1 a peer's record never arrived (bounded wait)
-__global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *local_rec, const P2pExchange X, int n_obs,
-                                                         DeviceBest *best, double *best_random, EvalResult *out,
-                                                         HostOut *host, unsigned long long ticket, int *out_status) {
+// returns false (in every thread) when the exchange failed
+__device__ __forceinline__ bool p2p_select_body(const unsigned char *local_rec, const P2pExchange &X, int n_obs,
+                                                DeviceBest *best, double *best_random, EvalResult *out, HostOut *host,
+                                                unsigned long long ticket, int *out_status) {
   __shared__ int s_fail;
   const int parity = (int)(X.seq & 1ull);
   const size_t bytes = argmin_record_bytes(n_obs);
@@ -996,7 +1029,7 @@ __global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *lo
       __threadfence_system();  // the status before the ticket
       if (host) host->seq[0] = ticket;  // wake the host; it reads out_status
     }
-    return;
+    return false;
   }
   // 4. replicated selection over the own block
   select_over_records(X.peers[X.rank] + (size_t)parity * kP2pMaxWorld * X.stride, X.stride, X.world, n_obs, best, best_random, out);
@@ -1009,6 +1042,12 @@ __global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *lo
     __threadfence_system();
     host->seq[0] = ticket;
   }
+  return true;
+}
+__global__ void __launch_bounds__(256) p2p_select_kernel(const unsigned char *local_rec, const P2pExchange X, int n_obs,
+                                                         DeviceBest *best, double *best_random, EvalResult *out,
+                                                         HostOut *host, unsigned long long ticket, int *out_status) {
+  p2p_select_body(local_rec, X, n_obs, best, best_random, out, host, ticket, out_status);
 }
 
 // ---- moveRealEEAgent (cf_manager.cpp:257-263 -> RealCfAgent::cfPlanner, cf_agent.cpp:343-366) ------------------
@@ -1028,10 +1067,13 @@ struct RealArgs {
   double goal[3];
   HostOut *host;          // zero-copy result + ticket (see HostOut), or null
   unsigned long long ticket;
+  // fused tick: the evaluate results go out with the real agent's, under ONE system-scope fence
+  const EvalResult *pub_eval;
+  const DeviceBest *pub_best;
 };
 
 // one warp
-__global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, const RealArgs R) {
+__device__ __forceinline__ void real_agent_body(const PlannerDev &P, const RealArgs &R) {
   __shared__ double fbuf[3 * 32];
   const Group<32> g;
   LiveObstacles obs;
@@ -1052,20 +1094,35 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   for (int s = 0; s < R.steps; ++s) {
     force = mk3(0.0, 0.0, 0.0);
     const v3 goal_vec = sub3(goal, p);
-    ExactMath em;  // scalar parts of the single real-agent step: built-in arithmetic
-    const StepNorms sn = step_norms(em, goal_vec, v, 1.0, false, k);
+    // scalar parts under FastMath (branch-free Newton refinements, bit-identical inside their proven range), the
+    // IEEE built-ins when an operand leaves it
+    ExactMath em;
+    FastMath fm;
+    StepNorms sn = step_norms(fm, goal_vec, v, 1.0, false, k);
+    v3 ghat, nv_unused;
+    step_units<false>(fm, goal_vec, v, sn, ghat, nv_unused);
+    if (__builtin_expect(fm.bad(), 0)) {
+      sn = step_norms(em, goal_vec, v, 1.0, false, k);
+      step_units<false>(em, goal_vec, v, sn, ghat, nv_unused);
+    }
     double k_goal_scale = 1.0;
     if (field_gate_open(sn.dist_goal, sn.vn, p, init_pos, k)) {
       double min_d, kgs_closest;
       bool has_closest;
-      v3 ghat, nv_unused;
-      step_units<false>(em, goal_vec, v, sn, ghat, nv_unused);
       field_pass<false, false>(g, obs, n_field, nullptr, n_field, type, p, v, goal_vec, sn, nv_unused, goal, ghat, k, known,
                         R.rot, R.best_random, fbuf, 0.0, force, min_d, has_closest, kgs_closest PMAF_T_PASS);
       if (has_closest && norm_gt(dot3(force, force), make_thr(1e-5))) k_goal_scale = kgs_closest;
       g.sync();
     }
-    finish_step(em, force, k_goal_scale, sn, obs.pos(R.n_obs - 1), R.delta_t, k, p, v);
+    {
+      const v3 p0 = p, v0 = v, f0 = force;
+      FastMath ff;
+      finish_step(ff, force, k_goal_scale, sn, obs.pos(R.n_obs - 1), R.delta_t, k, p, v);
+      if (__builtin_expect(ff.bad(), 0)) {
+        p = p0, v = v0, force = f0;
+        finish_step(em, force, k_goal_scale, sn, obs.pos(R.n_obs - 1), R.delta_t, k, p, v);
+      }
+    }
     if (g.gl == 0) {
       st3(R.path_out + 3 * s, p);
       if (R.host) st3(R.host->real_path + 3 * s, p);
@@ -1074,11 +1131,122 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
   if (g.gl == 0 && R.steps > 0) {
     st3(R.real->pos, p), st3(R.real->vel, v), st3(R.real->force, force);
     if (R.host) {
+      if (R.pub_eval) {
+        const EvalResult e = *R.pub_eval;
+        const DeviceBest b = *R.pub_best;
+        R.host->eval.best_index = e.best_index, R.host->eval.argmin_index = e.argmin_index;
+        R.host->eval.incumbent_changed = e.incumbent_changed, R.host->eval.pad = 0;
+        R.host->eval.best_cost = e.best_cost, R.host->eval.argmin_cost = e.argmin_cost;
+        R.host->best.present = b.present, R.host->best.id = b.id, R.host->best.type = b.type, R.host->best.pad = 0;
+      }
       st3(R.host->real.pos, p), st3(R.host->real.vel, v), st3(R.host->real.force, force), st3(R.host->real.init_pos, init_pos);
       __threadfence_system();
       R.host->seq[1] = R.ticket;
     }
   }
+}
+__global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, const RealArgs R) { real_agent_body(P, R); }
+
+// ---- the fused control tick ------------------------------------------------------------------------------------------------
+// pmaf_tick's device chain in ONE CTA instead of three or four dependent launches (evaluate [+ exchange] ->
+// real step -> reset): phase 1 evaluateAgents (cf_manager.cpp:293-356) — costs, serial-order argmin, for sharded
+// planners the peer-memory exchange and the replicated selection; phase 2 warp 0 moves the real agent
+// (cf_manager.cpp:257-263) while the other warps rebuild the obstacle image / nearest-neighbour table when the
+// obstacle list changed and pack the real agent's known flags; the agents' own reset (resetEEAgents,
+// cf_manager.cpp:246-255) happens in the prologue of the rollout that follows (PlannerDev::reset_in_prologue),
+// from the real agent's state this kernel leaves behind.
+struct TickArgs {
+  int eval_mode;        // 0: unsharded (finalize here), 1: local scan + peer-memory exchange + selection,
+                        // 2: selection over all-gathered records (NCCL fallback; the local scan ran before)
+  DeviceBest *best;
+  double *best_random;
+  ArgminRecord *rec;
+  EvalResult *eval;
+  HostOut *host;
+  unsigned long long eval_ticket;
+  P2pExchange xchg;     // eval_mode 1
+  const unsigned char *rec_all;  // eval_mode 2
+  int world;
+  int *p2p_status;
+  int rebuild_image;    // the obstacle list (or the broad-phase margin) changed since the image was built
+  int rebuild_nn;
+  uint32_t *known_bits, *known_keep;  // [known_words] packed flags of the real agent for the rollout's prologue
+};
+__global__ void __launch_bounds__(1024) tick_kernel(const PlannerDev P, const CostParams C, const TickArgs T,
+                                                    const RealArgs R, const ResetArgs S) {
+  asm volatile("griddepcontrol.launch_dependents;");  // the rollout may be scheduled now; it waits for this grid's end
+  bool ok = true;
+#if defined(PMAF_FAST_STATS)  // developer build: phase time stamps (ns) into step_counter[8..12]
+#define PMAF_STAMP(k) do { if (threadIdx.x == 0) P.step_counter[8 + (k)] = global_timer_ns(); } while (0)
+#else
+#define PMAF_STAMP(k) do { } while (0)
+#endif
+  PMAF_STAMP(0);
+  {
+    // Everything the dependent phases below will touch, into L2 now: after a cold start (or an L2 flush) every
+    // dependent first touch would otherwise be a DRAM round trip on the tick's critical path. Warp 0 takes what
+    // the real step needs, the other threads the agents' persistent rows the rollout's prologue reads.
+    const int n3 = R.n_obs * 3 * (int)sizeof(double);
+    if (threadIdx.x < 32) {
+      prefetch_l2(R.real, sizeof(RealState), threadIdx.x, 32), prefetch_l2(R.best, sizeof(DeviceBest), threadIdx.x, 32);
+      prefetch_l2(R.obs_pos, n3, threadIdx.x, 32), prefetch_l2(R.obs_vel, n3, threadIdx.x, 32);
+      prefetch_l2(R.obs_rad, n3 / 3, threadIdx.x, 32), prefetch_l2(R.known, R.n_obs, threadIdx.x, 32);
+      prefetch_l2(R.rot, n3, threadIdx.x, 32), prefetch_l2(R.best_random, n3, threadIdx.x, 32);
+    } else {
+      const int tid = threadIdx.x - 32, nthreads = blockDim.x - 32;
+      const size_t cap = (size_t)1 << 20;  // large populations: the first MiB of each (the rest streams anyway)
+      const size_t ng = (size_t)(P.first_agent + P.n_agents) * sizeof(double);
+      prefetch_l2(P.k_attr, ng < cap ? ng : cap, tid, nthreads), prefetch_l2(P.k_circ, ng < cap ? ng : cap, tid, nthreads);
+      prefetch_l2(P.k_repel, ng < cap ? ng : cap, tid, nthreads), prefetch_l2(P.k_damp, ng < cap ? ng : cap, tid, nthreads);
+      const size_t ni = (size_t)P.n_agents * 3 * sizeof(double), nk = (size_t)P.n_agents * P.known_words * sizeof(uint32_t);
+      prefetch_l2(P.init_pos, ni < cap ? ni : cap, tid, nthreads), prefetch_l2(P.known, nk < cap ? nk : cap, tid, nthreads);
+      prefetch_l2(P.runtime_zero, sizeof(unsigned), tid, nthreads);
+    }
+  }
+  if (T.eval_mode == 0) {
+    evaluate_body(P, C, T.best, T.best_random, T.rec, T.eval, 1, nullptr, 0ull);
+  } else if (T.eval_mode == 1) {
+    evaluate_body(P, C, T.best, T.best_random, T.rec, T.eval, 0, nullptr, 0ull);
+    __syncthreads();  // the record (global memory) is complete
+    ok = p2p_select_body(reinterpret_cast<const unsigned char *>(T.rec), T.xchg, P.n_obs, T.best, T.best_random, T.eval,
+                         nullptr, 0ull, T.p2p_status);
+  } else {
+    select_over_records(T.rec_all, argmin_record_bytes(P.n_obs), T.world, P.n_obs, T.best, T.best_random, T.eval);
+  }
+  __syncthreads();  // best / eval / best_random (global) are visible to the whole CTA
+  PMAF_STAMP(1);
+  if (!ok) {  // the real agent's ticket still has to arrive: the host waits for it, then reads the failure flag
+    if (threadIdx.x == 0 && R.host) {
+      __threadfence_system();  // the failure flag (p2p_select_body) before the ticket
+      R.host->seq[1] = R.ticket;
+    }
+    return;
+  }
+  const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  if (warp == 0) {
+    real_agent_body(P, R);
+  } else {
+    const int tid = threadIdx.x - 32, nthreads = blockDim.x - 32;
+    if (T.rebuild_image) build_obstacle_image(P, S, tid, nthreads);
+    if (T.rebuild_nn) build_nn_table(P, S, warp - 1, warps - 1);
+  }
+  if (blockDim.x == 32) {  // a one-warp CTA does everything in turn
+    if (T.rebuild_image) build_obstacle_image(P, S, threadIdx.x, 32);
+    if (T.rebuild_nn) build_nn_table(P, S, 0, 1);
+  }
+  PMAF_STAMP(2);
+  __syncthreads();  // real_known may have gained flags in the real step
+  // the real agent's known flags as bit words, one ballot per word (see pack_known_word)
+  for (int w = warp; w < P.known_words; w += warps) {
+    const int i = w * 32 + (threadIdx.x & 31);
+    const bool in_list = i < S.n_obs_update;
+    const unsigned bits = __ballot_sync(0xffffffffu, in_list && S.real_known[i] != 0);
+    const unsigned keep = __ballot_sync(0xffffffffu, !in_list);
+    if ((threadIdx.x & 31) == 0) T.known_bits[w] = bits, T.known_keep[w] = keep;
+  }
+  if (threadIdx.x == 0) P.step_counter[0] = 0ull;  // executed steps of the rollout that follows
+  PMAF_STAMP(3);
+#undef PMAF_STAMP
 }
 
 // The k cheapest agents of the last evaluate, in (cost, index) order — what the node's predicted-path

@@ -50,7 +50,7 @@ API_SYMBOLS = [
     "pmaf_get_num_prediction_steps", "pmaf_get_real_num_prediction_steps", "pmaf_get_agent_summaries",
     "pmaf_get_predicted_paths", "pmaf_get_predicted_path", "pmaf_get_agent_velocities",
     "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters", "pmaf_get_fast_stats", "pmaf_dry_run",
-    "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_timer_start", "pmaf_timer_stop",
+    "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_set_rollout_timing", "pmaf_timer_start", "pmaf_timer_stop",
     "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles", "pmaf_get_best_paths",
 ]
 
@@ -126,6 +126,7 @@ def load_library():
                                  C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, _ip, _dp, _dp]
     lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int, C.c_int]
     lib.pmaf_set_upload_dedup.argtypes = [H, C.c_int]
+    lib.pmaf_set_rollout_timing.argtypes = [H, C.c_int]
     lib.pmaf_timer_start.argtypes = [H]
     lib.pmaf_timer_stop.argtypes = [H, _dp]
     lib.pmaf_flush_l2.argtypes = [H]
@@ -260,21 +261,25 @@ class CfManager:
         return best.value, p, v
 
     def dry_run(self, ticks, obs_pos, obs_vel, obs_rad, n_feed, delta_t, k_goal_dist, k_path_len, k_safe_dist,
-                k_workspace, ws_limits, feed_frequency=100.0, wait_rollout=False, flush_l2=False, profile=None):
+                k_workspace, ws_limits, feed_frequency=100.0, wait_rollout=False, flush_l2=False, profile=None,
+                tick_times=None):
         """`ticks` planCallbacks in the library's C++ host loop (pmaf_dry_run) on HOST obstacle arrays; obs_pos is
         advanced in place by the obstacle feed. Returns (seconds inside the ticks, best[ticks], next_pos, next_vel)."""
         assert obs_pos.dtype == np.float64 and obs_pos.flags["C_CONTIGUOUS"]
         ov, orad = _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
         best = np.zeros(max(ticks, 1), dtype=np.int32)
         npos, nvel = np.zeros((max(ticks, 1), 3)), np.zeros((max(ticks, 1), 3))
-        sec = (C.c_double * 7)()
-        flags = (1 if wait_rollout else 0) | (2 if flush_l2 else 0) | (4 if profile is not None else 0)
+        sec = (C.c_double * (7 + max(ticks, 0)))()
+        flags = (1 if wait_rollout else 0) | (2 if flush_l2 else 0) | (4 if profile is not None else 0) | \
+            (8 if tick_times is not None else 0)
         self._check(self.lib.pmaf_dry_run(self.h, int(ticks), len(orad), _d(obs_pos), _d(ov), _d(orad), int(n_feed),
                                           float(feed_frequency), float(delta_t), float(k_goal_dist), float(k_path_len),
                                           float(k_safe_dist), float(k_workspace), _d(_f64(ws_limits, (6,))), flags,
                                           sec, _i(best), _d(npos), _d(nvel)))
         if profile is not None:  # per-call wall time: stop, evaluate, move_real, get + reset, start, final wait
             profile[:] = [sec[k] for k in range(1, 7)]
+        if tick_times is not None:  # wall time of every tick
+            tick_times[:] = [sec[7 + t] for t in range(ticks)]
         return sec[0], best[:ticks], npos[:ticks], nvel[:ticks]
 
     # ---- getters ----------------------------------------------------------------------------------
@@ -374,6 +379,10 @@ class CfManager:
         names = ["unusable_or_candidates", "start_threshold", "range_distance_chain", "first_detection_general",
                  "range_force_chain", "force_threshold", "sentinel_in_reach", "acceleration_clamp", "range_integrator"]
         return {n: int(out[i]) for i, n in enumerate(names)}
+
+    def set_rollout_timing(self, on):
+        """CUDA events around every rollout kernel (counters' rollout times); off = production setting."""
+        self._check(self.lib.pmaf_set_rollout_timing(self.h, int(bool(on))))
 
     def set_upload_dedup(self, dedup):
         self._check(self.lib.pmaf_set_upload_dedup(self.h, 1 if dedup else 0))
