@@ -373,6 +373,11 @@ def sharded_parity(env, args, name="near326_switching", ticks=3):
 
 
 def run_ours(args, rank, world, local_rank):
+    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner comes out on
+    # fd 1 whatever NCCL_DEBUG_FILE says) goes to stderr; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
 
     if not torch.cuda.is_available():
@@ -417,7 +422,8 @@ def run_ours(args, rank, world, local_rank):
                                     "sample": f"{ticks} closed-loop control ticks of {sc.name} (all "
                                               f"{sc.num_agents} agents), pooled driver on {cores} host threads, "
                                               f"{seconds:.1f} s"}
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if env.dist:
         env.dist.destroy_process_group()
 
