@@ -242,10 +242,22 @@ def measure(env, args, sc1, steps, warmup, seeded_random=False):
         mgr.seed_random_vecs(sc.seed)
     loop.plan_begin(mgr, sc, random_vecs=not seeded_random)
 
+    n_feed = sc.num_obstacles - 1 if feed.active else 0
+    state = {"resident": False}
+
     def tick():
-        out = mgr.tick(feed.pos, feed.vel, feed.rad, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
-                       sc.k_workspace, sc.ws_limits)
-        feed.step()
+        # moving scenes: the obstacle feed (dynamic_obstacle_node's integration step) runs on the device-resident
+        # list (pmaf_feed_obstacles, applied inside the tick kernel); the list crosses the bus once
+        if state["resident"] and feed.active:
+            out = mgr.tick(None, None, None, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist, sc.k_workspace,
+                           sc.ws_limits)
+        else:
+            out = mgr.tick(feed.pos, feed.vel, feed.rad, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                           sc.k_workspace, sc.ws_limits)
+            state["resident"] = True
+        feed.step()  # the host copy stays in step: the e2e leg below passes it
+        if feed.active:
+            mgr.feed_obstacles(n_feed, feed.frequency)
         return out
 
     def timed_ticks(n):
@@ -287,7 +299,6 @@ def measure(env, args, sc1, steps, warmup, seeded_random=False):
     mgr.stop_prediction()
     e0 = mgr.counters()
     env.barrier()
-    n_feed = sc.num_obstacles - 1 if feed.active else 0
     tick_s = []
     e2e_s, _, _, _ = mgr.dry_run(steps, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
                                  sc.k_path_len, sc.k_safe_dist, sc.k_workspace, sc.ws_limits,

@@ -164,10 +164,23 @@ int pmaf_move_real_agent(pmaf_planner *p, int n_obs, const double *obs_pos, cons
 int pmaf_reset_agents(pmaf_planner *p, const double pos[3], const double vel[3], int n_obs,
                       const double *obs_pos, const double *obs_vel, const double *obs_rad);
 
+/* The obstacle feed on the device: dynamic_obstacle_node's integration step (src/dynamic_obstacle_node.cpp:
+ * 352-369: `cur_pos.at(i) += cur_vel.at(i) / frequency` for the published obstacles 0..n_feed-1, the sentinel is
+ * never published) followed by obstacleCallback's overwrite of the planner's list (src/panda_bimanual_control.cpp:
+ * 302-309), applied to the DEVICE-resident live list — the one the last call that took an obstacle list
+ * uploaded — so that a moving scene costs no host->device copy per tick. The same IEEE operations run on the
+ * library's host mirror of the list: a caller that advances its own copy identically and keeps passing it finds
+ * it recognised as unchanged (no upload), a caller of pmaf_tick may pass obs_pos = obs_vel = obs_rad = NULL
+ * instead. The step is applied by the next pmaf_tick inside its tick kernel (no extra launch), or by a small
+ * kernel of its own before any other consumer of the list. */
+int pmaf_feed_obstacles(pmaf_planner *p, int n_feed, double frequency);
+
 /* One whole planCallback tick (node:329-369) as a device-resident chain with a single host
  * synchronisation: [set_real_position if measured_pos != NULL] -> stop -> evaluate -> move real
  * agent (1 step, gains of the best agent) -> reset agents (from the real agent's new state) ->
- * start. Outputs: best index, next position (the `goals` message) and next velocity. */
+ * start. Outputs: best index, next position (the `goals` message) and next velocity.
+ * obs_pos = obs_vel = obs_rad = NULL: use the device-resident live list (n_obs entries) as the last upload /
+ * pmaf_feed_obstacles left it. */
 int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs, const double *obs_pos,
               const double *obs_vel, const double *obs_rad, double delta_t, double k_goal_dist,
               double k_path_len, double k_safe_dist, double k_workspace, const double ws_limits[6],
@@ -229,6 +242,8 @@ int pmaf_get_costs(pmaf_planner *p, double *costs /* [n_agents] */);
 #define PMAF_DRY_RUN_FLUSH_L2 2
 #define PMAF_DRY_RUN_PROFILE 4
 #define PMAF_DRY_RUN_TICK_TIMES 8 /* seconds must hold 7 + ticks doubles; seconds[7 + t] = wall time of tick t */
+#define PMAF_DRY_RUN_DEVICE_FEED 16 /* the feed between ticks also runs on the device (pmaf_feed_obstacles): the
+                                     * calls' host lists are recognised as unchanged and not uploaded */
 int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_pos, const double *obs_vel, const double *obs_rad,
                  int n_feed, double feed_frequency, double delta_t, double k_goal_dist, double k_path_len,
                  double k_safe_dist, double k_workspace, const double ws_limits[6], int flags, double *seconds,

@@ -103,6 +103,39 @@ def zero_relative_velocity(sc):
     return run
 
 
+def message_shaped_lists(sc, ticks):
+    """Every call that takes an obstacle list gets the O-1 entries an `Obstacles.msg` carries — the obstacle
+    node never publishes the sentinel (dynamic_obstacle_node.cpp:317,356) — instead of the planner's full
+    list: moveRealEEAgent then treats the last PUBLISHED obstacle as the repulsion source (cf_agent.cpp:110-144,
+    159-181 loop over the list they are given), resetEEAgents / setObstacles touch only the passed entries
+    (cf_agent.cpp:63-70) and leave the agents' own sentinel and its known flag alone."""
+
+    def run(planner):
+        feed = loop.ObstacleFeed(sc)
+        loop.plan_begin(planner, sc)
+        rec = dict(best=[], next_pos=[], next_vel=[], steps=[], length=[], min_obs_dist=[], reached=[], goal_dist=[])
+        for _ in range(ticks):
+            op, ov, orad = feed.pos[:-1], feed.vel[:-1], feed.rad[:-1]
+            planner.stop_prediction()
+            best = planner.evaluate_agents(op, ov, orad, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist, sc.k_workspace,
+                                           sc.ws_limits)
+            planner.move_real_agent(op, ov, orad, sc.delta_t, 1, best)
+            p, v = planner.get_next_position(), planner.get_next_velocity()
+            planner.reset_agents(p, v, op, ov, orad)
+            planner.start_prediction()
+            planner.stop_prediction()
+            s = planner.get_agent_summaries()
+            rec["best"].append(best), rec["next_pos"].append(p), rec["next_vel"].append(v)
+            for k in ("steps", "length", "min_obs_dist", "reached"):
+                rec[k].append(s[k].copy())
+            rec["goal_dist"].append(planner.get_dist_from_goal())
+            feed.step()
+        return _finish(planner, {k: np.array(v) for k, v in rec.items()}, sc)
+
+    run.scenario = sc
+    return run
+
+
 def _with_obstacles(sc, pos, rad, vel=None, **kw):
     pos = np.array(list(pos) + [[100.0, 100.0, 100.0]], dtype=np.float64)
     rad = np.array(list(rad) + [0.1], dtype=np.float64)
@@ -166,6 +199,8 @@ def all_cases(golden_dir=None):
         "near326_reinit_random_incumbent": reinit(near(326), 65, [-0.6, 0.2, 0.8]),
         "position_feedback": feedback(S.small_random(8, num_agents=8, horizon=100), 15),
         "zero_rel_velocity": zero_relative_velocity(S.small_random(9, num_agents=8, num_obstacles=4, horizon=50)),
+        "message_lists_moving": message_shaped_lists(S.small_random(103, moving=True, num_agents=10, num_obstacles=11), 25),
+        "message_lists_static": message_shaped_lists(near(326), 40),
     }
     if golden_dir is not None:
         c.update(task_cases(golden_dir))

@@ -136,6 +136,8 @@ struct pmaf_planner {
   double margin_scale_static = 0.0;  // largest |coordinate| among goal, start, obstacles (broad_phase_margin)
   bool image_current = false;        // the staging image matches the agents' obstacle copy, layout and margin
   bool live_changed = false;         // upload_live sent a new list since the image was built
+  int pending_feed_n = 0;            // pmaf_feed_obstacles not yet applied on the device
+  double pending_feed_freq = 0.0;
   DevBuf<uint32_t> known_bits, known_keep;  // packed real-agent flags for the rollout's in-prologue reset
   // rollout bookkeeping
   bool rollout_pending = false;
@@ -1023,9 +1025,38 @@ extern "C" int pmaf_evaluate_agents(pmaf_planner *p, int n_obs, const double *ob
   return 0;
 }
 
+// apply a pending obstacle feed on the device (consumers other than pmaf_tick's kernel)
+static int flush_pending_feed(pmaf_planner *p) {
+  if (p->pending_feed_n <= 0) return 0;
+  const int n = p->pending_feed_n;
+  p->pending_feed_n = 0;
+  return launch(p, feed_kernel, dim3(1), dim3(256), 0, p->live_pos.p, (const double *)p->live_vel.p, n, p->pending_feed_freq);
+}
+
+extern "C" int pmaf_feed_obstacles(pmaf_planner *p, int n_feed, double frequency) {
+  ENTER(p);
+  NEED_INIT(p);
+  const size_t n = p->h_live.size() / 7;  // entries of the list the device holds
+  REQUIRE(n > 0, PMAF_ERR_STATE, "pmaf_feed_obstacles: no obstacle list has been passed yet (evaluate / move / reset / tick)");
+  REQUIRE(n == (size_t)p->O, PMAF_ERR_STATE,
+          "pmaf_feed_obstacles: the device-resident list has %zu entries, the planner %d (partial lists are re-uploaded)", n, p->O);
+  REQUIRE(n_feed >= 0 && (size_t)n_feed <= n && frequency > 0.0, PMAF_ERR_ARG, "pmaf_feed_obstacles: n_feed=%d frequency=%g",
+          n_feed, frequency);
+  if (n_feed == 0) return 0;
+  if (int rc = flush_pending_feed(p)) return rc;  // an earlier step nobody consumed yet
+  // host mirror: the same IEEE operations as the device (no contraction on either side)
+  double *pos = p->h_live.data();
+  const double *vel = pos + 3 * n;
+  for (int i = 0; i < 3 * n_feed; ++i) pos[i] += vel[i] / frequency;
+  p->pending_feed_n = n_feed, p->pending_feed_freq = frequency;
+  p->live_changed = true;
+  return 0;
+}
+
 // upload a live obstacle list unless it is byte-identical to the last one uploaded
 static int upload_live(pmaf_planner *p, int n_obs, const double *obs_pos, const double *obs_vel,
                        const double *obs_rad) {
+  if (int rc = flush_pending_feed(p)) return rc;
   const size_t n = (size_t)n_obs;
   std::vector<double> &last = p->h_live;
   const bool same = p->upload_dedup && last.size() == 7 * n && memcmp(last.data(), obs_pos, 3 * n * sizeof(double)) == 0 &&
@@ -1144,14 +1175,28 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
                          int *best_index, double next_pos[3], double next_vel[3]) {
   ENTER(p);
   NEED_INIT(p);
-  REQUIRE(obs_pos && obs_vel && obs_rad && ws_limits, PMAF_ERR_ARG, "pmaf_tick: null argument");
+  REQUIRE(ws_limits, PMAF_ERR_ARG, "pmaf_tick: null argument");
   REQUIRE(n_obs >= 1 && n_obs <= p->O, PMAF_ERR_ARG, "pmaf_tick: n_obs=%d (planner has %d obstacles)", n_obs, p->O);
+  const bool device_list = !obs_pos && !obs_vel && !obs_rad;
+  REQUIRE(device_list || (obs_pos && obs_vel && obs_rad), PMAF_ERR_ARG, "pmaf_tick: pass all three obstacle arrays or none");
+  if (device_list) {  // the device-resident list, as the last upload / pmaf_feed_obstacles left it (host mirror: h_live)
+    REQUIRE(p->h_live.size() == 7 * (size_t)n_obs, PMAF_ERR_STATE,
+            "pmaf_tick: no device-resident obstacle list of %d entries (pass the arrays once first)", n_obs);
+    obs_pos = p->h_live.data(), obs_vel = obs_pos + 3 * (size_t)n_obs, obs_rad = obs_pos + 6 * (size_t)n_obs;
+  }
   if (measured_pos) {
     if (int rc = pmaf_set_real_position(p, measured_pos)) return rc;
   }
   // the previous rollout is ordered before everything below by the stream; no host wait for it
   if (int rc = harvest_timing(p, p->roll_slot, false)) return rc;
-  if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+  // a pending obstacle feed rides along in the tick kernel when the caller's list is the fed one
+  int feed_n = 0;
+  if (p->pending_feed_n > 0 && (device_list || (p->upload_dedup && p->h_live.size() == 7 * (size_t)n_obs &&
+                                                memcmp(p->h_live.data(), obs_pos, 3 * (size_t)n_obs * sizeof(double)) == 0)))
+    feed_n = p->pending_feed_n, p->pending_feed_n = 0;
+  if (!device_list) {
+    if (int rc = upload_live(p, n_obs, obs_pos, obs_vel, obs_rad)) return rc;
+  }
   const CostParams C = make_cost(k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits);
   // Two launches per tick: tick_kernel (evaluateAgents [+ best-agent exchange], moveRealEEAgent, obstacle image /
   // known flags for the reset) and the rollout, whose prologue is resetEEAgents.
@@ -1167,6 +1212,7 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   }
   d = make_dev(p);  // the image layout may have changed
   TickArgs T{};
+  T.feed_n = feed_n, T.feed_frequency = p->pending_feed_freq, T.feed_pos = p->live_pos.p, T.feed_vel = p->live_vel.p;
   T.best = p->best.p, T.best_random = p->best_random.p, T.rec = reinterpret_cast<ArgminRecord *>(p->rec.p);
   T.eval = p->eval.p, T.host = p->h_out_dev, T.world = p->world;
   T.p2p_status = (int *)&p->h_out_dev->p2p_fail;
@@ -1292,6 +1338,9 @@ extern "C" int pmaf_dry_run(pmaf_planner *p, int ticks, int n_obs, double *obs_p
       if (next_vel) next_vel[3 * t + i] = vel[i];
     }
     for (int i = 0; i < 3 * n_feed; ++i) obs_pos[i] += obs_vel[i] / feed_frequency;
+    if ((flags & PMAF_DRY_RUN_DEVICE_FEED) && n_feed > 0) {  // the same step on the device-resident list
+      if (int rc = pmaf_feed_obstacles(p, n_feed, feed_frequency)) return rc;
+    }
   }
   if (seconds) *seconds = total;
   return 0;

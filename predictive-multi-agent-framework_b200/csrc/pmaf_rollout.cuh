@@ -1155,7 +1155,20 @@ __global__ void __launch_bounds__(32) real_agent_kernel(const PlannerDev P, cons
 // obstacle list changed and pack the real agent's known flags; the agents' own reset (resetEEAgents,
 // cf_manager.cpp:246-255) happens in the prologue of the rollout that follows (PlannerDev::reset_in_prologue),
 // from the real agent's state this kernel leaves behind.
+// dynamic_obstacle_node's integration step (dynamic_obstacle_node.cpp:357) on the device-resident live list
+__device__ __forceinline__ void feed_obstacles(double *live_pos, const double *live_vel, int n_feed, double frequency,
+                                               int tid, int nthreads) {
+  for (int i = tid; i < 3 * n_feed; i += nthreads) live_pos[i] += live_vel[i] / frequency;
+}
+__global__ void __launch_bounds__(256) feed_kernel(double *live_pos, const double *live_vel, int n_feed, double frequency) {
+  feed_obstacles(live_pos, live_vel, n_feed, frequency, threadIdx.x, blockDim.x);
+}
+
 struct TickArgs {
+  int feed_n;           // > 0: a pending obstacle feed (pmaf_feed_obstacles) is applied first
+  double feed_frequency;
+  double *feed_pos;
+  const double *feed_vel;
   int eval_mode;        // 0: unsharded (finalize here), 1: local scan + peer-memory exchange + selection,
                         // 2: selection over all-gathered records (NCCL fallback; the local scan ran before)
   DeviceBest *best;
@@ -1182,6 +1195,8 @@ __global__ void __launch_bounds__(1024) tick_kernel(const PlannerDev P, const Co
 #define PMAF_STAMP(k) do { } while (0)
 #endif
   PMAF_STAMP(0);
+  // a pending obstacle feed: before anything reads the live list (the barrier after the evaluate phase orders it)
+  if (T.feed_n > 0) feed_obstacles(T.feed_pos, T.feed_vel, T.feed_n, T.feed_frequency, threadIdx.x, blockDim.x);
   {
     // Everything the dependent phases below will touch, into L2 now: after a cold start (or an L2 flush) every
     // dependent first touch would otherwise be a DRAM round trip on the tick's critical path. Warp 0 takes what

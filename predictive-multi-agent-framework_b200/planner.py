@@ -44,7 +44,7 @@ API_SYMBOLS = [
     "pmaf_last_error", "pmaf_version", "pmaf_create", "pmaf_destroy", "pmaf_set_shard", "pmaf_nccl_unique_id", "pmaf_nccl_init", "pmaf_set_nccl_comm", "pmaf_p2p_export", "pmaf_p2p_import",
     "pmaf_init", "pmaf_seed_random_vecs", "pmaf_set_random_vecs", "pmaf_get_random_vecs",
     "pmaf_set_initial_position", "pmaf_set_real_position", "pmaf_start_prediction", "pmaf_stop_prediction",
-    "pmaf_evaluate_agents", "pmaf_move_real_agent", "pmaf_reset_agents", "pmaf_tick", "pmaf_get_num_agents",
+    "pmaf_evaluate_agents", "pmaf_move_real_agent", "pmaf_reset_agents", "pmaf_feed_obstacles", "pmaf_tick", "pmaf_get_num_agents",
     "pmaf_get_next_position", "pmaf_get_next_velocity", "pmaf_get_ee_force", "pmaf_get_goal_position",
     "pmaf_get_initial_position", "pmaf_get_dist_from_goal", "pmaf_get_best_agent_type", "pmaf_get_best_agent_id",
     "pmaf_get_num_prediction_steps", "pmaf_get_real_num_prediction_steps", "pmaf_get_agent_summaries",
@@ -102,6 +102,7 @@ def load_library():
                                          _dp, _ip]
     lib.pmaf_move_real_agent.argtypes = [H, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int]
     lib.pmaf_reset_agents.argtypes = [H, _dp, _dp, C.c_int, _dp, _dp, _dp]
+    lib.pmaf_feed_obstacles.argtypes = [H, C.c_int, C.c_double]
     lib.pmaf_tick.argtypes = [H, _dp, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double,
                               C.c_double, _dp, _ip, _dp, _dp]
     lib.pmaf_get_num_agents.argtypes = [H, _ip]
@@ -250,19 +251,29 @@ class CfManager:
 
     def tick(self, obs_pos, obs_vel, obs_rad, delta_t, k_goal_dist, k_path_len, k_safe_dist, k_workspace, ws_limits,
              measured_position=None):
-        """One whole planCallback as a device-resident chain (pmaf_tick)."""
-        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
+        """One whole planCallback as a device-resident chain (pmaf_tick). obs_pos = obs_vel = obs_rad = None: the
+        device-resident list as the last upload / feed_obstacles left it."""
         best = C.c_int()
         p, v = np.zeros(3), np.zeros(3)
         meas = _d(_f64(measured_position, (3,))) if measured_position is not None else None
+        if obs_pos is None:
+            self._check(self.lib.pmaf_tick(self.h, meas, self.O, None, None, None, float(delta_t), float(k_goal_dist),
+                                           float(k_path_len), float(k_safe_dist), float(k_workspace),
+                                           _d(_f64(ws_limits, (6,))), C.byref(best), _d(p), _d(v)))
+            return best.value, p, v
+        op, ov, orad = _f64(obs_pos, (-1, 3)), _f64(obs_vel, (-1, 3)), _f64(obs_rad, (-1,))
         self._check(self.lib.pmaf_tick(self.h, meas, len(orad), _d(op), _d(ov), _d(orad), float(delta_t),
                                        float(k_goal_dist), float(k_path_len), float(k_safe_dist), float(k_workspace),
                                        _d(_f64(ws_limits, (6,))), C.byref(best), _d(p), _d(v)))
         return best.value, p, v
 
+    def feed_obstacles(self, n_feed, frequency=100.0):
+        """The obstacle node's integration step on the device-resident live list (pmaf_feed_obstacles)."""
+        self._check(self.lib.pmaf_feed_obstacles(self.h, int(n_feed), float(frequency)))
+
     def dry_run(self, ticks, obs_pos, obs_vel, obs_rad, n_feed, delta_t, k_goal_dist, k_path_len, k_safe_dist,
                 k_workspace, ws_limits, feed_frequency=100.0, wait_rollout=False, flush_l2=False, profile=None,
-                tick_times=None):
+                tick_times=None, device_feed=False):
         """`ticks` planCallbacks in the library's C++ host loop (pmaf_dry_run) on HOST obstacle arrays; obs_pos is
         advanced in place by the obstacle feed. Returns (seconds inside the ticks, best[ticks], next_pos, next_vel)."""
         assert obs_pos.dtype == np.float64 and obs_pos.flags["C_CONTIGUOUS"]
@@ -271,7 +282,7 @@ class CfManager:
         npos, nvel = np.zeros((max(ticks, 1), 3)), np.zeros((max(ticks, 1), 3))
         sec = (C.c_double * (7 + max(ticks, 0)))()
         flags = (1 if wait_rollout else 0) | (2 if flush_l2 else 0) | (4 if profile is not None else 0) | \
-            (8 if tick_times is not None else 0)
+            (8 if tick_times is not None else 0) | (16 if device_feed else 0)
         self._check(self.lib.pmaf_dry_run(self.h, int(ticks), len(orad), _d(obs_pos), _d(ov), _d(orad), int(n_feed),
                                           float(feed_frequency), float(delta_t), float(k_goal_dist), float(k_path_len),
                                           float(k_safe_dist), float(k_workspace), _d(_f64(ws_limits, (6,))), flags,

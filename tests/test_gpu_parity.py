@@ -141,6 +141,53 @@ def test_cpp_dry_run_loop_matches_reference_golden(name):
         p.close()
 
 
+@pytest.mark.parametrize("name", ["moving0", "moving1", "moving2_freq2", "task_sim_kobo_dyn_spheres1"])
+def test_device_side_obstacle_feed_matches_reference_golden(name):
+    """f2: the obstacle node's integration step runs on the device-resident list (pmaf_feed_obstacles, applied inside
+    the tick kernel); after the first tick no obstacle byte crosses the bus, and every tick still equals the
+    reference build's golden record (whose feed ran on the host, dynamic_obstacle_node.cpp:352-369)."""
+    sc = CASES[name].scenario
+    want = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    ticks = len(want["best"])
+    n_feed = sc.num_obstacles - 1
+    for mode in ("tick_device_list", "tick_host_list", "dry_run"):
+        p = _planner()
+        loop.plan_begin(p, sc)
+        feed = loop.ObstacleFeed(sc)
+        h2d_after_first = None
+        if mode == "dry_run":
+            p.dry_run(1, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                      sc.k_workspace, sc.ws_limits, feed_frequency=feed.frequency, device_feed=True)
+            h2d_after_first = p.counters()["h2d_bytes"]
+            _, best, pos, vel = p.dry_run(ticks - 1, feed.pos, feed.vel, feed.rad, n_feed, sc.delta_t, sc.k_goal_dist,
+                                          sc.k_path_len, sc.k_safe_dist, sc.k_workspace, sc.ws_limits,
+                                          feed_frequency=feed.frequency, device_feed=True)
+            got = dict(best=best, next_pos=pos, next_vel=vel)
+            ref = dict(best=want["best"][1:], next_pos=want["next_pos"][1:], next_vel=want["next_vel"][1:])
+        else:
+            best, pos, vel = [], [], []
+            for t in range(ticks):
+                if t == 0 or mode == "tick_host_list":
+                    b, x, v = p.tick(feed.pos, feed.vel, feed.rad, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                                     sc.k_workspace, sc.ws_limits)
+                else:
+                    b, x, v = p.tick(None, None, None, sc.delta_t, sc.k_goal_dist, sc.k_path_len, sc.k_safe_dist,
+                                     sc.k_workspace, sc.ws_limits)
+                if t == 0:
+                    h2d_after_first = p.counters()["h2d_bytes"]
+                best.append(b), pos.append(x), vel.append(v)
+                feed.step()  # the caller's own copy (passed again in tick_host_list mode: recognised as unchanged)
+                p.feed_obstacles(n_feed, feed.frequency)
+            got = dict(best=np.array(best), next_pos=np.array(pos), next_vel=np.array(vel))
+            ref = dict(best=want["best"], next_pos=want["next_pos"], next_vel=want["next_vel"])
+        p.stop_prediction()
+        got["steps"] = p.get_agent_summaries()["steps"]
+        ref["steps"] = want["steps"][-1]
+        assert_bit_identical(got, ref, keys=list(got), ctx=f"{name} {mode}: ")
+        assert p.counters()["h2d_bytes"] == h2d_after_first, f"{name} {mode}: obstacle bytes were uploaded after the first tick"
+        p.close()
+
+
 def _oracle():
     from oracle import cpu_planners
 
