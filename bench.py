@@ -64,53 +64,97 @@ def workload_config(sc, n_gpus, extra=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed regions (B200_PROFILING.md's clocks line).
+    In-process NVML from a thread when `pynvml` is importable — a query costs microseconds; an `nvidia-smi -lms` child
+    process re-initialises NVML state on every sample and was measured to stall this process's CUDA calls for
+    milliseconds a few times per second — else the nvidia-smi loop of the recipe."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.025
 
     def __init__(self, gpu_index=0):
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), None
+        self.p = self.f = self.thread = None
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self._stop = False
+
+            def loop_():
+                while not self._stop:
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = int(get_reasons(h))
+                        for name, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(self.PERIOD_S)
+
+            import threading
+
+            self.thread = threading.Thread(target=loop_, daemon=True)
+            self.thread.start()
+            self.how = f"in-process NVML, {int(1e3 * self.PERIOD_S)} ms period"
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
+            self.how = "nvidia-smi -lms 100"
         except OSError:
             pass
 
     def wait_ready(self, timeout=8.0):
         """nvidia-smi's start-up (driver / NVML initialisation) can stall CUDA calls of other processes for
-        milliseconds: wait for its first sample before anything is timed."""
+        milliseconds: wait for the first sample before anything is timed."""
         t0 = time.time()
-        while self.p is not None and time.time() - t0 < timeout:
-            if os.path.getsize(self.f.name) > 0:
+        while time.time() - t0 < timeout:
+            if (self.thread is not None and self.sm) or (self.p is not None and os.path.getsize(self.f.name) > 0):
                 break
-            time.sleep(0.05)
+            if self.thread is None and self.p is None:
+                break
+            time.sleep(0.02)
         return self
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.1)
-        self.p.terminate()
-        self.p.wait()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1])), mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[5:9]):
-                if v.strip().lower() == "active":
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons),
-                "span": "all timed regions of this run (headline, e2e and sub-records), 50 ms period"}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join()
+        elif self.p is not None:
+            time.sleep(0.1)
+            self.p.terminate()
+            self.p.wait()
+            self.f.flush()
+            rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+            os.unlink(self.f.name)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for r in rows:
+                try:
+                    self.sm.append(float(r[1])), self.mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(self.sm), "reasons": sorted(self.reasons),
+                "how": self.how, "span": "all timed regions of this run (headline, roofline pass, e2e and sub-records)"}
 
 
 def measured_peaks():

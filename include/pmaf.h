@@ -306,6 +306,36 @@ int pmaf_selftest_math(pmaf_planner *p, uint64_t samples, uint64_t seed, uint64_
  * their last rollout, out[64][12]; all zero unless libpmaf was built with -DPMAF_SECTION_TIMERS. */
 int pmaf_get_section_cycles(pmaf_planner *p, long long *out);
 
+/* ---- downstream kinematics ---------------------------------------------------------------------
+ * Dual-quaternion kinematics of the Franka Panda as the reference's controller evaluates it every cycle for one
+ * robot on the CPU — pose (fkm) and pose Jacobian through dqrobotics' DQ_SerialManipulator with the modified-DH
+ * table of src/franka_robot.cpp:6-22 (CoSTPController::calculateControlPreliminaries, src/costp_controller.cpp:
+ * 111-126) and the geometric Jacobian geomJ (src/costp_controller.cpp:465-492) — on the device. dqrobotics is
+ * not vendored by the reference: the algebra follows its published definitions and PARITY WITH A dqrobotics
+ * BUILD IS UNPINNED (oracle/dq_oracle.c). Dual quaternions are 8 doubles: primary w x y z, dual w x y z;
+ * base_dq is the arm's base frame (r + eps/2 p r, src/franka_robot.cpp:14-20). */
+int pmaf_dq_kinematics(pmaf_planner *p, const double base_dq[8], const double q[7], double pose[8],
+                       double pose_jacobian[56] /* 8 x 7 row-major */, double geom_jacobian[42] /* 6 x 7 row-major */);
+/* Joint limits of the Panda as the controller holds them (src/costp_controller.cpp:41-44). */
+void pmaf_panda_joint_limits(double q_lo[7], double q_hi[7]);
+
+typedef struct {
+  double max_pos_err;        /* largest residual |path point - end-effector position| after the point's step */
+  double min_joint_margin;   /* smallest distance of any joint to its nearer limit along the path (< 0: violated) */
+  double min_manipulability; /* smallest sqrt(det(Jt Jt^T)) of the translation Jacobian along the path */
+  int feasible;              /* every point tracked within tol_pos, inside the joint limits */
+  int first_bad_point;       /* first point that failed, -1 if none */
+  double q_final[7];
+} pmaf_path_score;
+/* Batched feasibility score of the predicted end-effector paths, on the device-resident paths of the last
+ * rollout (nothing is copied out but the scores): one damped-least-squares step per path point from q_start,
+ * dq = Jt^T (Jt Jt^T + damping I)^-1 e (the form of src/costp_controller.cpp:134-135).
+ * k <= 0: every local agent, out[n_agents], agent_index may be NULL. k >= 1 (<= 64): the k cheapest agents of the
+ * last evaluate in (cost, index) order as pmaf_get_best_paths, agent_index[k] receives their global indices
+ * (-1 = fewer agents than k; that score is of an empty path). */
+int pmaf_score_paths(pmaf_planner *p, int k, const double base_dq[8], const double q_start[7], const double q_lo[7],
+                     const double q_hi[7], double damping, double tol_pos, int *agent_index, pmaf_path_score *out);
+
 #ifdef __cplusplus
 }
 #endif

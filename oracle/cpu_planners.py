@@ -253,3 +253,55 @@ class RefPlanner(_CpuPlanner):
 class OraclePlanner(_CpuPlanner):
     PREFIX = "cforacle"
     LIB = ORACLE_LIB
+
+
+# ---- downstream dual-quaternion kinematics (dq_oracle.c, PARITY UNPINNED) -----------------
+DQ_LIB = os.path.join(_HERE, "libdqoracle.so")
+
+
+class DqPathScore(C.Structure):
+    _fields_ = [("max_pos_err", C.c_double), ("min_joint_margin", C.c_double), ("min_manipulability", C.c_double),
+                ("feasible", C.c_int), ("first_bad_point", C.c_int), ("q_final", C.c_double * 7)]
+
+
+class DqOracle:
+    """ctypes front end of oracle/dq_oracle.c."""
+
+    def __init__(self):
+        if not os.path.exists(DQ_LIB):
+            build("oracle")
+        self.lib = C.CDLL(DQ_LIB)
+        self.lib.dqo_fkm.argtypes = [_dp, _dp, _dp]
+        self.lib.dqo_pose_jacobian.argtypes = [_dp, _dp, _dp]
+        self.lib.dqo_translation.argtypes = [_dp, _dp]
+        self.lib.dqo_geom_jacobian.argtypes = [_dp, _dp, _dp]
+        self.lib.dqo_score_path.argtypes = [_dp, _dp, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double, C.POINTER(DqPathScore)]
+
+    def fkm(self, base, q):
+        out = np.zeros(8)
+        self.lib.dqo_fkm(_d(_f64(base, (8,))), _d(_f64(q, (7,))), _d(out))
+        return out
+
+    def pose_jacobian(self, base, q):
+        out = np.zeros((8, 7))
+        self.lib.dqo_pose_jacobian(_d(_f64(base, (8,))), _d(_f64(q, (7,))), _d(out))
+        return out
+
+    def translation(self, x):
+        out = np.zeros(3)
+        self.lib.dqo_translation(_d(_f64(x, (8,))), _d(out))
+        return out
+
+    def geom_jacobian(self, base, q):
+        out = np.zeros((6, 7))
+        self.lib.dqo_geom_jacobian(_d(_f64(base, (8,))), _d(_f64(q, (7,))), _d(out))
+        return out
+
+    def score_path(self, base, q_start, path, q_lo, q_hi, damping=1e-3, tol_pos=1e-3):
+        path = _f64(path, (-1, 3))
+        out = DqPathScore()
+        self.lib.dqo_score_path(_d(_f64(base, (8,))), _d(_f64(q_start, (7,))), _d(path), len(path), _d(_f64(q_lo, (7,))),
+                                _d(_f64(q_hi, (7,))), float(damping), float(tol_pos), C.byref(out))
+        return dict(max_pos_err=out.max_pos_err, min_joint_margin=out.min_joint_margin,
+                    min_manipulability=out.min_manipulability, feasible=out.feasible,
+                    first_bad_point=out.first_bad_point, q_final=np.array(list(out.q_final)))

@@ -18,6 +18,7 @@
 
 #include "../../include/pmaf.h"
 #include "pmaf_rollout.cuh"
+#include "pmaf_dq.cuh"
 
 using namespace pmaf;
 
@@ -1797,5 +1798,74 @@ extern "C" int pmaf_get_best_paths(pmaf_planner *p, int k, int stride, int max_p
     n_points[r] = m;
     agent_index[r] = a + p->first_agent;
   }
+  return 0;
+}
+
+// ---- downstream kinematics -----------------------------------------------------------------------
+extern "C" void pmaf_panda_joint_limits(double q_lo[7], double q_hi[7]) {
+  // src/costp_controller.cpp:41-44
+  const double lo[7] = {-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973};
+  const double hi[7] = {2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973};
+  for (int i = 0; i < 7; ++i) q_lo[i] = lo[i], q_hi[i] = hi[i];
+}
+
+extern "C" int pmaf_dq_kinematics(pmaf_planner *p, const double base_dq[8], const double q[7], double pose[8],
+                                  double pose_jacobian[56], double geom_jacobian[42]) {
+  ENTER(p);
+  REQUIRE(base_dq && q && pose && pose_jacobian && geom_jacobian, PMAF_ERR_ARG, "pmaf_dq_kinematics: null argument");
+  DevBuf<double> d;
+  CU(d.resize(8 + 7 + 8 + 56 + 42));
+  double h[15];
+  memcpy(h, base_dq, 8 * sizeof(double)), memcpy(h + 8, q, 7 * sizeof(double));
+  CU(cudaMemcpyAsync(d.p, h, sizeof h, cudaMemcpyHostToDevice, p->stream));
+  if (int rc = launch(p, dq_probe_kernel, dim3(1), dim3(32), 0, (const double *)d.p, (const double *)(d.p + 8), d.p + 15,
+                      d.p + 23, d.p + 79))
+    return rc;
+  double out[8 + 56 + 42];
+  CU(cudaMemcpyAsync(out, d.p + 15, sizeof out, cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  memcpy(pose, out, 8 * sizeof(double)), memcpy(pose_jacobian, out + 8, 56 * sizeof(double));
+  memcpy(geom_jacobian, out + 64, 42 * sizeof(double));
+  d.release();
+  return 0;
+}
+
+extern "C" int pmaf_score_paths(pmaf_planner *p, int k, const double base_dq[8], const double q_start[7], const double q_lo[7],
+                                const double q_hi[7], double damping, double tol_pos, int *agent_index, pmaf_path_score *out) {
+  ENTER(p);
+  NEED_INIT(p);
+  static_assert(sizeof(pmaf_path_score) == sizeof(PathScore), "pmaf_path_score mirrors PathScore");
+  REQUIRE(base_dq && q_start && q_lo && q_hi && out && k <= 64 && damping > 0.0, PMAF_ERR_ARG,
+          "pmaf_score_paths: bad argument (k <= 64, damping > 0)");
+  REQUIRE(k <= 0 || agent_index, PMAF_ERR_ARG, "pmaf_score_paths: agent_index is required for k >= 1");
+  REQUIRE(k <= 0 || p->have_cost, PMAF_ERR_STATE, "pmaf_score_paths: no evaluate_agents yet");
+  if (int rc = finish_rollout(p)) return rc;
+  const int n = k > 0 ? k : p->A;
+  DevBuf<int> d_idx;
+  DevBuf<PathScore> d_out;
+  CU(d_out.resize(n));
+  PlannerDev d = make_dev(p);
+  if (k > 0) {  // the k cheapest agents of the last evaluate (local indices, -1 padded)
+    CU(d_idx.resize(k));
+    const int threads = p->A >= 1024 ? 1024 : std::max(32, ((p->A + 31) / 32) * 32);
+    if (int rc = launch(p, topk_kernel, dim3(1), dim3(threads), 0, d, k, d_idx.p)) return rc;
+  }
+  ScoreArgs S{};
+  S.paths = p->paths.p, S.n_path = p->n_path.p, S.max_steps = p->H, S.agent_index = k > 0 ? d_idx.p : nullptr, S.n = n;
+  for (int i = 0; i < 8; ++i) S.base[i] = base_dq[i];
+  for (int i = 0; i < 7; ++i) S.q_start[i] = q_start[i], S.q_lo[i] = q_lo[i], S.q_hi[i] = q_hi[i];
+  S.damping = damping, S.tol_pos = tol_pos, S.out = d_out.p;
+  if (int rc = launch(p, dq_score_kernel, dim3((n + 127) / 128), dim3(128), 0, S)) return rc;
+  if (int rc = fetch(p, out, d_out.p, (size_t)n * sizeof(PathScore))) return rc;
+  if (k > 0) {
+    if (int rc = fetch(p, agent_index, d_idx.p, (size_t)k * sizeof(int))) return rc;
+  }
+  CU(cudaStreamSynchronize(p->stream));
+  if (k > 0)
+    for (int r = 0; r < k; ++r)
+      if (agent_index[r] >= 0) agent_index[r] += p->first_agent;
+  if (k <= 0 && agent_index)
+    for (int a = 0; a < n; ++a) agent_index[a] = p->first_agent + a;
+  d_idx.release(), d_out.release();
   return 0;
 }

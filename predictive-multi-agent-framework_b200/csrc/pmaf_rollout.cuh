@@ -389,6 +389,10 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   if (FAST && have_agent) {  // the agent's rotation-vector row into L1 now: its first uses sit on the critical path
     const char *row = reinterpret_cast<const char *>(rot_row);
     for (int off = g.gl * 128; off < P.n_obs * 24; off += LPA * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + off));
+    if (type == RANDOM_AGENT) {  // ... and its random vectors: every first detection reads one (:559-566)
+      const char *rnd = reinterpret_cast<const char *>(random_row);
+      for (int off = g.gl * 128; off < P.n_obs * 24; off += LPA * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(rnd + off));
+    }
   }
   FastConsts fc;
   if (FAST) fc = make_fast_consts(k, type, rz);
@@ -1216,6 +1220,7 @@ __global__ void __launch_bounds__(1024) tick_kernel(const PlannerDev P, const Co
       const size_t ni = (size_t)P.n_agents * 3 * sizeof(double), nk = (size_t)P.n_agents * P.known_words * sizeof(uint32_t);
       prefetch_l2(P.init_pos, ni < cap ? ni : cap, tid, nthreads), prefetch_l2(P.known, nk < cap ? nk : cap, tid, nthreads);
       prefetch_l2(P.runtime_zero, sizeof(unsigned), tid, nthreads);
+      if (!T.rebuild_image) prefetch_l2(S.image, P.img.bytes, tid, nthreads);
     }
   }
   if (T.eval_mode == 0) {

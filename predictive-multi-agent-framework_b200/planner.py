@@ -31,6 +31,11 @@ class PmafError(RuntimeError):
         self.status = status
 
 
+class PathScore(C.Structure):
+    _fields_ = [("max_pos_err", C.c_double), ("min_joint_margin", C.c_double), ("min_manipulability", C.c_double),
+                ("feasible", C.c_int), ("first_bad_point", C.c_int), ("q_final", C.c_double * 7)]
+
+
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("collectives", C.c_uint64), ("rollouts", C.c_uint64), ("agent_steps", C.c_uint64), ("agent_steps_total", C.c_uint64),
                 ("last_rollout_ms", C.c_double), ("rollout_ms_total", C.c_double), ("h2d_bytes", C.c_uint64),
@@ -52,6 +57,7 @@ API_SYMBOLS = [
     "pmaf_get_planned_trajectory", "pmaf_get_obstacle_state", "pmaf_get_costs", "pmaf_get_counters", "pmaf_get_fast_stats", "pmaf_dry_run",
     "pmaf_set_tuning", "pmaf_set_upload_dedup", "pmaf_set_rollout_timing", "pmaf_timer_start", "pmaf_timer_stop",
     "pmaf_flush_l2", "pmaf_measure_fp64_peak", "pmaf_selftest_math", "pmaf_get_section_cycles", "pmaf_get_best_paths",
+    "pmaf_dq_kinematics", "pmaf_panda_joint_limits", "pmaf_score_paths",
 ]
 
 
@@ -125,6 +131,10 @@ def load_library():
     lib.pmaf_get_fast_stats.argtypes = [H, C.POINTER(C.c_uint64)]
     lib.pmaf_dry_run.argtypes = [H, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double,
                                  C.c_double, C.c_double, C.c_double, _dp, C.c_int, _dp, _ip, _dp, _dp]
+    lib.pmaf_dq_kinematics.argtypes = [H, _dp, _dp, _dp, _dp, _dp]
+    lib.pmaf_panda_joint_limits.argtypes = [_dp, _dp]
+    lib.pmaf_panda_joint_limits.restype = None
+    lib.pmaf_score_paths.argtypes = [H, C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, _ip, C.POINTER(PathScore)]
     lib.pmaf_set_tuning.argtypes = [H, C.c_int, C.c_int, C.c_int]
     lib.pmaf_set_upload_dedup.argtypes = [H, C.c_int]
     lib.pmaf_set_rollout_timing.argtypes = [H, C.c_int]
@@ -418,6 +428,35 @@ class CfManager:
         out = (C.c_uint64 * 5)()
         self._check(self.lib.pmaf_selftest_math(self.h, int(samples), int(seed), out))
         return dict(zip(("sqrt_mismatch", "div_mismatch", "div3_mismatch", "flagged", "compared"), list(out)))
+
+    # ---- downstream kinematics ------------------------------------------------
+    def dq_kinematics(self, base_dq, q):
+        """Pose (8), pose Jacobian (8 x 7) and geometric Jacobian (6 x 7) of the Panda at q, on the device."""
+        pose, J, G = np.zeros(8), np.zeros((8, 7)), np.zeros((6, 7))
+        self._check(self.lib.pmaf_dq_kinematics(self.h, _d(_f64(base_dq, (8,))), _d(_f64(q, (7,))), _d(pose), _d(J), _d(G)))
+        return pose, J, G
+
+    def panda_joint_limits(self):
+        lo, hi = np.zeros(7), np.zeros(7)
+        self.lib.pmaf_panda_joint_limits(_d(lo), _d(hi))
+        return lo, hi
+
+    def score_paths(self, base_dq, q_start, k=0, q_lo=None, q_hi=None, damping=1e-3, tol_pos=1e-3):
+        """Feasibility scores of the predicted paths of the last rollout (k = 0: every local agent; k >= 1: the k
+        cheapest agents of the last evaluate). Returns (agent_index[n], dict of arrays)."""
+        lo, hi = self.panda_joint_limits()
+        lo = _f64(q_lo, (7,)) if q_lo is not None else lo
+        hi = _f64(q_hi, (7,)) if q_hi is not None else hi
+        n = k if k > 0 else self.A
+        idx = np.zeros(n, dtype=np.int32)
+        out = (PathScore * n)()
+        self._check(self.lib.pmaf_score_paths(self.h, int(k), _d(_f64(base_dq, (8,))), _d(_f64(q_start, (7,))), _d(lo), _d(hi),
+                                              float(damping), float(tol_pos), _i(idx), out))
+        rec = dict(max_pos_err=np.array([o.max_pos_err for o in out]), min_joint_margin=np.array([o.min_joint_margin for o in out]),
+                   min_manipulability=np.array([o.min_manipulability for o in out]),
+                   feasible=np.array([o.feasible for o in out]), first_bad_point=np.array([o.first_bad_point for o in out]),
+                   q_final=np.array([list(o.q_final) for o in out]))
+        return idx, rec
 
     def get_best_paths(self, k, stride=1, max_points=None):
         """The k cheapest agents of the last evaluate and their (decimated) paths."""
