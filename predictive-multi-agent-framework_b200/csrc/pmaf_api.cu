@@ -1250,7 +1250,7 @@ extern "C" int pmaf_tick(pmaf_planner *p, const double *measured_pos, int n_obs,
   S.obs_pos = p->obs_pos.p, S.obs_vel = p->obs_vel.p, S.obs_rad = p->obs_rad.p, S.real_known = p->real_known.p;
   S.image = p->image.p, S.margin = p->margin;
   // one warp for the real agent, the rest for the costs / the image (at least one more warp)
-  const int threads = std::min(1024, std::max(64, ((p->A + 31) / 32) * 32 + 32));
+  const int threads = std::min(256, std::max(64, ((p->A + 31) / 32) * 32 + 32));
   if (int rc = launch(p, tick_kernel, dim3(1), dim3(threads), 0, d, C, T, R, S)) return rc;
   p->image_current = true, p->live_changed = false;
   p->fused_valid = true;

@@ -15,16 +15,20 @@ constexpr int kFastSumUnroll = 8;
 //   cand[cand_stride], uint32 known[known_words]
 // Per-group strides are padded so that the groups of one warp (2 / 4 agents per warp) fall into different banks
 // when they read their own list / staging buffer at the same offset: stride = 4 words (16 B) mod 32 words.
-__host__ __device__ inline uint32_t rollout_cand_stride(int n_obs) { return (uint32_t)(((n_obs + 63) & ~63) + 8); }
+__host__ __device__ inline uint32_t rollout_cand_stride(int n_obs, int lanes_per_agent) {
+  if (lanes_per_agent >= 32) return (uint32_t)((n_obs + 7) & ~7);  // one group per warp: nothing to separate
+  return (uint32_t)(((n_obs + 63) & ~63) + 8);
+}
 __host__ __device__ inline uint32_t rollout_fbuf_stride(int lanes_per_agent) {
   const uint32_t n = 3u * (uint32_t)(lanes_per_agent + kFastSumUnroll);  // doubles
+  if (lanes_per_agent >= 32) return n;
   return n + ((34u - (n & 15u)) & 15u);  // (2 * stride) mod 32 words == 4: stride mod 16 doubles == 2
 }
 __host__ __device__ inline size_t rollout_smem_bytes(const ObstacleImage &img, int groups, int lanes_per_agent,
                                                      int known_words) {
   size_t b = 16 + img.bytes;
   b += (size_t)groups * rollout_fbuf_stride(lanes_per_agent) * sizeof(double);
-  b += (size_t)groups * rollout_cand_stride(img.n_obs) * sizeof(uint16_t);
+  b += (size_t)groups * rollout_cand_stride(img.n_obs, lanes_per_agent) * sizeof(uint16_t);
   b += (size_t)groups * known_words * sizeof(uint32_t);
   return (b + 15) & ~(size_t)15;
 }
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   double *fbuf_all = reinterpret_cast<double *>(img + P.img.bytes);
   const uint32_t fbuf_stride = rollout_fbuf_stride(LPA);
   uint16_t *cand_all = reinterpret_cast<uint16_t *>(fbuf_all + (size_t)groups * fbuf_stride);
-  const uint32_t cand_stride = rollout_cand_stride(P.n_obs);
+  const uint32_t cand_stride = rollout_cand_stride(P.n_obs, LPA);
   uint32_t *known_all = reinterpret_cast<uint32_t *>(cand_all + (size_t)groups * cand_stride);
 
   // stage the obstacle set: one TMA bulk copy per CTA, completion on an mbarrier
@@ -389,10 +393,6 @@ __global__ void __launch_bounds__(OCC == 1 ? 256 : 128, OCC) rollout_kernel(cons
   if (FAST && have_agent) {  // the agent's rotation-vector row into L1 now: its first uses sit on the critical path
     const char *row = reinterpret_cast<const char *>(rot_row);
     for (int off = g.gl * 128; off < P.n_obs * 24; off += LPA * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + off));
-    if (type == RANDOM_AGENT) {  // ... and its random vectors: every first detection reads one (:559-566)
-      const char *rnd = reinterpret_cast<const char *>(random_row);
-      for (int off = g.gl * 128; off < P.n_obs * 24; off += LPA * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(rnd + off));
-    }
   }
   FastConsts fc;
   if (FAST) fc = make_fast_consts(k, type, rz);
@@ -1189,7 +1189,9 @@ struct TickArgs {
   int rebuild_nn;
   uint32_t *known_bits, *known_keep;  // [known_words] packed flags of the real agent for the rollout's prologue
 };
-__global__ void __launch_bounds__(1024) tick_kernel(const PlannerDev P, const CostParams C, const TickArgs T,
+// at most 256 threads: the real agent's step (warp 0) needs the full register file — at 1024 threads per CTA the
+// kernel is held to 64 registers and the step spills (measured: it is the longest phase of the kernel)
+__global__ void __launch_bounds__(256, 1) tick_kernel(const PlannerDev P, const CostParams C, const TickArgs T,
                                                     const RealArgs R, const ResetArgs S) {
   asm volatile("griddepcontrol.launch_dependents;");  // the rollout may be scheduled now; it waits for this grid's end
   bool ok = true;
