@@ -459,10 +459,14 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_sub and args.workload == "c2":
         names = ["c3", "c5", "c4s"] if world == 1 else ["c4s"]
         for name in names:
-            r, m = measure(env, args, WORKLOADS[name](), SUB_TICKS, 3, seeded_random=(world > 1))
-            m.close()
-            r["roofline"] = roofline(r, fp64_peak, peaks, peak_src, measured_traffic(name) if world == 1 else None)
-            r.update({"name": name if world == 1 else "c4", "metric": METRIC, "unit": "agent-steps/s", "n_gpus": world})
+            label = name if world == 1 else "c4"
+            try:  # a failing sub-record must not take the headline line with it
+                r, m = measure(env, args, WORKLOADS[name](), SUB_TICKS, 3, seeded_random=(world > 1))
+                m.close()
+                r["roofline"] = roofline(r, fp64_peak, peaks, peak_src, measured_traffic(name) if world == 1 else None)
+                r.update({"name": label, "metric": METRIC, "unit": "agent-steps/s", "n_gpus": world})
+            except Exception as e:  # noqa: BLE001
+                r = {"name": label, "error": f"{type(e).__name__}: {e}"}
             subs.append(r)
     line["workloads"] = subs
     line["clocks"] = sampler.stop() if sampler else None

@@ -2,26 +2,19 @@
 partitioning, the NCCL-id exchange plumbing, and the best-agent exchange protocol (per-rank record
 -> all-gather -> replicated serial selection), which must equal the reference's serial argmin with
 hysteresis over the whole population — ties, NaN costs, incumbents on other ranks included."""
-import os
-import socket
-
 import numpy as np
 import pytest
-import torch.distributed as dist
-import torch.multiprocessing as mp
 
+from mp_util import init_gloo, run_ranks
 from pmaf_b200 import sharded
 
 
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+def _worker(rank, world, init_file, q):
+    import os
+    import sys
 
-
-def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist = init_gloo(rank, world, init_file)
     try:
         # 1. the id exchange: every rank ends up with rank 0's 128 bytes
         ident = sharded.exchange_nccl_id(lambda: bytes(range(128)), rank)
@@ -54,16 +47,8 @@ def _worker(rank, world, port, q):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_selection_equals_serial_scan(world):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=120) for _ in procs]
-    for p in procs:
-        p.join(timeout=30)
-    assert all(msg == "ok" for _, msg in results), results
+    results = run_ranks(_worker, world, timeout=120)
+    assert len(results) == world and all(msg == "ok" for _, msg in results), results
 
 
 def test_shard_ranges_partition_the_population():
