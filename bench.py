@@ -285,6 +285,7 @@ def measure(env, args, sc1, steps, warmup, seeded_random=False):
     if seeded_random:  # large sharded populations: the library draws each rank's vectors itself (shard-independent streams)
         mgr.seed_random_vecs(sc.seed)
     loop.plan_begin(mgr, sc, random_vecs=not seeded_random)
+    env.barrier()  # ranks finish their (differently long) initialisation before the first exchange waits on a peer
 
     n_feed = sc.num_obstacles - 1 if feed.active else 0
     state = {"resident": False}

@@ -98,7 +98,7 @@ int pmaf_set_nccl_comm(pmaf_planner *p, void *nccl_comm);
  * world given to import must equal the shard's when evaluate runs. Every import needs a fresh export on ALL
  * ranks (the export zeroes the block's sequence numbers and drops earlier mappings): a second import without
  * one returns PMAF_ERR_STATE. If import fails (no peer access), the NCCL path stays in use.
- * Failure: a peer whose record does not arrive within 2 s makes evaluate_agents / tick return PMAF_ERR_NCCL.
+ * Failure: a peer whose record does not arrive within 10 s makes evaluate_agents / tick return PMAF_ERR_NCCL.
  * That is FATAL for the whole sharded group — ranks that did complete the tick have moved on, so the replicas of
  * the incumbent best agent may differ: every later evaluate on this handle fails the same way until all ranks
  * have called pmaf_init again and re-done the export / import handshake. */

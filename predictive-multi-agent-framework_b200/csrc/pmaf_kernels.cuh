@@ -12,10 +12,11 @@
 //                adds a zero force, and is ignored by attractorForceScaling), so only candidates
 //                go on. Candidates are compacted, in obstacle order, into a per-group list.
 //   narrow phase (fp64, candidates only, one lane per candidate): the reference's circForce body
-//                (cf_agent.cpp:76-106) bit for bit; forces are then summed across lanes in
-//                obstacle-index order (serial fp64 adds on values fetched by warp shuffle) so that
-//                the sum has the reference's rounding; min distance and the closest obstacle are
-//                warp-shuffle reductions (exact: min / lexicographic min).
+//                (cf_agent.cpp:76-106) bit for bit; forces are then summed in obstacle-index order
+//                (contributions staged in shared memory by rank, serial fp64 adds front to back) so
+//                that the sum has the reference's rounding; min distance and the closest obstacle are
+//                redux.sync reductions on the integer order of non-negative doubles (exact: min /
+//                lexicographic min), xor-shuffle butterflies for groups narrower than a warp.
 //   scalar part  (gate, repulsion from the sentinel, attraction, integrator, cost accumulators):
 //                replicated in every lane of the group.
 #pragma once

@@ -1,7 +1,7 @@
 // pmaf_math.cuh — binary64 building blocks of the circular-field agent step, in the operation
 // order of the reference (citations: /root/reference/src/bimanual_planning_ros/src/cf_agent.cpp
 // unless noted). Every function is __host__ __device__ so that the same source can be checked on
-// the CPU (tests/host_math_check.cpp) and runs inside the sm_100a kernels.
+// the CPU (tests/host_step_check.cu, tests/host_exp_check.cu) and runs inside the sm_100a kernels.
 //
 // Exactness contract: compile with -fmad=false (device) / -ffp-contract=off (host). The
 // reference is built for default x86-64 (no FMA), Eigen 3.3 fixed-size vectors:

@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(256) global_select_kernel(const unsigned char 
 // parity: a rank can be at most one tick ahead of another (its next selection needs everyone's next
 // record), so a slot is never overwritten before its reader is done.
 constexpr int kP2pMaxWorld = 16;
-constexpr unsigned long long kP2pWaitNs = 2000000000ull;  // 2 s: longest wait for a peer's record
+constexpr unsigned long long kP2pWaitNs = 10000000000ull;  // 10 s: longest wait for a peer's record
 struct P2pExchange {
   unsigned char *peers[kP2pMaxWorld];  // every rank's exchange block as mapped into this process (own block included)
   int rank, world;

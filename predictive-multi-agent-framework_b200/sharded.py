@@ -4,17 +4,19 @@ Agents are independent within a control tick (cf_manager.cpp:118-123: one thread
 owns the contiguous block [r*A/W, (r+1)*A/W) of the global population; agent types and gains follow
 the GLOBAL index. Obstacles and the real agent are replicated (every rank steps its own replica of
 the real agent — deterministic, so the replicas stay bit-identical). The only exchange is the
-best-agent selection: ONE NCCL all-gather per evaluate of
+best-agent selection: per evaluate ONE record per rank
 
     { min_cost, incumbent_cost, cost_agent0, min_index, owns_incumbent, random_vecs[O][3] }
 
-(40 + 24*O bytes per rank), enqueued by libpmaf on the planner's stream between its local-scan
-kernel and the replicated selection kernel; no host round trip. `local_record` /
+(40 + 24*O bytes), stored by every rank straight into every peer's cudaIpc-mapped exchange block over
+NVLink inside the tick kernel (local scan, exchange, replicated selection and the real agent's step are
+one launch), or — when peer mapping is unavailable — gathered by one NCCL all-gather that libpmaf
+enqueues on the planner's stream; no host round trip either way. `local_record` /
 `select_global_best` below restate that protocol on the host; the gloo tests use them to check
 that the sharded selection equals the reference's serial scan over the whole population.
 
-torch.distributed is plumbing only: it distributes the NCCL unique id (and, in bench.py, the
-timing reductions).
+torch.distributed is plumbing only: it distributes the NCCL unique id and the cudaIpc handles (and, in
+bench.py, the timing reductions).
 """
 from __future__ import annotations
 
