@@ -39,6 +39,40 @@ def test_facade_compiles_and_links():
         assert f" {name}(" in hdr, name
 
 
+REF_PKG = "/root/reference/src/bimanual_planning_ros"
+
+
+def test_reference_planner_node_compiles_against_the_facade():
+    """f1's claim, exercised: the reference's planner node — src/panda_bimanual_control.cpp, UNMODIFIED, read where
+    it lies — passes the compiler's full semantic analysis (`g++ -fsyntax-only`: every CfManager call the node makes
+    is resolved against include/pmaf/cf_manager.hpp) with the one-line replacement of cf_manager.h that
+    INTEGRATION.md §1 describes. ROS, dynamic_reconfigure, actionlib, the generated messages and Eigen are absent
+    from the image: tests/cpp/ros_stubs/ declares their surface (declarations only, nothing is linked or run).
+    Needs the reference checkout, so it runs in the dev container only."""
+    src = os.path.join(REF_PKG, "src", "panda_bimanual_control.cpp")
+    if not os.path.exists(src):
+        pytest.skip("reference sources not present")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    cmd = [cxx, "-std=c++17", "-fsyntax-only", "-w", "-H", f"-I{ROOT}/tests/cpp/ros_stubs", f"-I{ROOT}/include",
+           f"-I{ROOT}/tests/cpp/stubs", f"-I{REF_PKG}/include", src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    included = r.stderr
+    assert "include/pmaf/cf_manager.hpp" in included and "include/pmaf.h" in included  # the facade, not ...
+    assert f"{REF_PKG}/include/bimanual_planning_ros/cf_manager.h" not in included    # ... the reference's class
+    assert f"{REF_PKG}/include/bimanual_planning_ros/cf_agent.h" not in included
+    assert f"{REF_PKG}/include/bimanual_planning_ros/panda_bimanual_control.h" in included  # the node's own header is the reference's
+    # and the check bites: without a member the node calls, the same command fails
+    broken = os.path.join(BUILD, "broken_facade")
+    os.makedirs(os.path.join(broken, "pmaf"), exist_ok=True)
+    hdr = open(os.path.join(ROOT, "include", "pmaf", "cf_manager.hpp")).read()
+    assert "  void resetEEAgents(" in hdr
+    open(os.path.join(broken, "pmaf", "cf_manager.hpp"), "w").write(hdr.replace("  void resetEEAgents(", "  void resetEEAgentsRenamed("))
+    shutil.copy(os.path.join(ROOT, "include", "pmaf.h"), os.path.join(broken, "pmaf.h"))
+    bad = subprocess.run([c if c != f"-I{ROOT}/include" else f"-I{broken}" for c in cmd], capture_output=True, text=True)
+    assert bad.returncode != 0 and "resetEEAgents" in bad.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_host_program_matches_reference_golden():
     exe = _compile()
