@@ -3,7 +3,10 @@
     python tools/ncu_lines.py report.ncu-rep agent_steps_per_launch [top]
 
 Prints, per file:line, the warp instructions executed per agent-step (inlined code is attributed to the
-line it came from), the FP64 share and the average active threads.
+line it came from), the FP64 share, the average active threads and the share of the stall samples.
+The correlated view lists a SASS instruction under every source line it is attributed to (call site and
+inlined callee), so the per-line counts add up to ~20 % more than the kernel's instruction total: read them as a
+ranking, and take totals from tools/summarize_ncu.py.
 """
 import collections
 import csv
