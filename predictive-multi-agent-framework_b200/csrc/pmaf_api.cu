@@ -699,6 +699,7 @@ extern "C" int pmaf_init(pmaf_planner *p, const double goal[3], double delta_t, 
     p->best_n_obs = (int)O;
   }
   p->h_live.clear();
+  p->pending_feed_n = 0;  // a feed nobody consumed belongs to the list of the previous init
 
   // gains (global), agents' obstacle copy, random vectors
   p->h_obs_pos.assign(obs_pos, obs_pos + O * 3);
