@@ -61,3 +61,51 @@ def test_shard_ranges_partition_the_population():
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             sizes = [e - f for f, e in r]
             assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchange_protocol_model_never_reads_an_overwritten_slot(world):
+    """Model of the peer-memory exchange (csrc/pmaf_rollout.cuh: p2p_select_body): every rank stores its record into
+    slot [parity][rank] of every peer's block, publishes the tick's sequence number per peer, waits for all flags of
+    the tick in its own block, then reads all slots. Two buffers alternate by tick parity. The claim behind it: a rank
+    can be at most one tick ahead of any other (its next selection needs everyone's next record), so a slot is never
+    overwritten before its reader is done. Ranks are threads with random skew; every read must carry the reader's
+    own sequence number."""
+    import random
+    import threading
+    import time
+
+    ticks = 300
+    slots = [[[(-1, -1)] * world for _ in range(2)] for _ in range(world)]  # [owner block][parity][writer rank] = (seq, payload)
+    flags = [[[0] * world for _ in range(2)] for _ in range(world)]
+    errors = []
+
+    def rank_main(r):
+        rng = random.Random(1000 + r)
+        for t in range(ticks):
+            seq = t + 1
+            parity = seq & 1
+            if rng.random() < 0.2:
+                time.sleep(rng.random() * 1e-3)  # skew: some ranks arrive late, others race ahead
+            for peer in range(world):  # 1. the record into every rank's block
+                slots[peer][parity][r] = (seq, 1000 * r + t)
+            for peer in range(world):  # 2. publish
+                flags[peer][parity][r] = seq
+            t0 = time.time()
+            while any(flags[r][parity][w] != seq for w in range(world)):  # 3. wait for everyone's record of this tick
+                if time.time() - t0 > 20:
+                    errors.append((r, t, "timeout"))
+                    return
+                time.sleep(0)
+            for w in range(world):  # 4. the replicated selection reads every slot
+                got = slots[r][parity][w]
+                if got != (seq, 1000 * w + t):
+                    errors.append((r, t, w, got))
+                    return
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not errors, errors[:5]
